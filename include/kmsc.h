@@ -1,0 +1,158 @@
+/* kmsc.h -- C ABI of libkmsc, the B200 (sm_100a) data-parallel core for
+ * kkty/kmer-sets-compression's `kmerset-multiple-compress` hot path.
+ *
+ * The reference is a header-only C++17 template library with no FFI of its own
+ * (SURVEY.md section 8b); the drop-in boundary is therefore this C ABI, bound
+ * by the C++17 facade in kmer-sets-compression_b200/host/ whose classes mirror
+ * the reference's (KmerSet, KmerCounter, KmerSetCompact, KmerSetSet). Every
+ * entry point names the reference interface it replaces (paths relative to
+ * /root/reference/). Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative KMSC_E_* code otherwise;
+ *    kmsc_last_error() returns the calling thread's last message.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with KMSC_E_CUDA.
+ *  - A k-mer is the reference's 2K-bit value (lib/core/kmer.h:22-46): A=0 C=1
+ *    G=2 T=3, first base most significant. bucket = value >> (2K-N),
+ *    key = value mod 2^(2K-N) (lib/core/kmer_set.h:22-43).
+ *  - A device set (kmsc_set) is the CSR form of the reference's bucketed set:
+ *    offs[2^N + 1] and keys[] ascending inside each bucket. key_bytes is
+ *    sizeof(KeyType): 2, 4 or 8 (uint16/uint32/uint64 as in
+ *    src/kmerset-multiple-compress.cc:149-157; uint64 for K=31).
+ *  - Host buffers belong to the caller; device buffers belong to the library
+ *    until the matching *_free. Calls are synchronous at return unless the name
+ *    ends in _async / _device (those enqueue on the context's stream).
+ *  - One kmsc_ctx = one GPU + one stream; drive it from one host thread.
+ *    Multi-GPU = one context per process/rank, sets restricted to that rank's
+ *    bucket range, partial matrices summed by the caller's all-reduce.
+ */
+#ifndef KMSC_H_
+#define KMSC_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMSC_OK 0
+#define KMSC_E_INVALID (-1) /* bad argument */
+#define KMSC_E_CUDA (-2)    /* CUDA runtime/driver error, or no device */
+#define KMSC_E_NOMEM (-3)
+#define KMSC_E_FORMAT (-4)  /* malformed input text (FASTA / SPSS) */
+#define KMSC_E_STATE (-5)
+
+typedef struct kmsc_ctx kmsc_ctx;
+typedef struct kmsc_set kmsc_set;
+
+const char* kmsc_last_error(void);
+const char* kmsc_version(void);
+
+/* ---- context ---------------------------------------------------------------- */
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to
+ * let the library create its own non-blocking stream. */
+int kmsc_ctx_create(int device, void* stream, kmsc_ctx** out);
+void kmsc_ctx_destroy(kmsc_ctx* ctx);
+int kmsc_ctx_sync(kmsc_ctx* ctx);
+void* kmsc_ctx_stream(kmsc_ctx* ctx);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t kmsc_ctx_launch_count(kmsc_ctx* ctx);
+
+/* ---- device sets: KmerSet<K,N,KeyType> as CSR --------------------------------- */
+/* Host CSR -> device set. offs: int64[2^N+1]; keys: key_bytes each, ascending
+ * within each bucket (duplicates allowed, as GetSampledKmerSet may produce,
+ * lib/core/kmer_set_compact.h:120-203). Replaces building a KmerSet by Add()
+ * (lib/core/kmer_set.h:77-83). */
+int kmsc_set_from_csr(kmsc_ctx* ctx, int K, int N, int key_bytes, const int64_t* offs,
+                      const void* keys, kmsc_set** out);
+/* Same, from ascending 2K-bit k-mer values (uint64), e.g. KmerSet::Find output. */
+int kmsc_set_from_kmers(kmsc_ctx* ctx, int K, int N, int key_bytes, const uint64_t* kmers,
+                        int64_t n, kmsc_set** out);
+/* device set -> host CSR (either pointer may be NULL). */
+int kmsc_set_to_csr(kmsc_ctx* ctx, const kmsc_set* set, int64_t* offs, void* keys);
+void kmsc_set_free(kmsc_ctx* ctx, kmsc_set* set);
+/* KmerSet::Size (lib/core/kmer_set.h:62-68) and KmerSet::Hash = XOR of all 2K-bit
+ * values (lib/core/kmer_set.h:224-244, kmer.h:211), computed on the device. */
+int kmsc_set_size(kmsc_ctx* ctx, const kmsc_set* set, int64_t* size);
+int kmsc_set_hash(kmsc_ctx* ctx, const kmsc_set* set, uint64_t* hash);
+int kmsc_set_info(const kmsc_set* set, int* K, int* N, int* key_bytes, int64_t* n_keys);
+
+/* ---- P2: SPSS text -> device set ------------------------------------------------ */
+/* Replaces KmerSetCompact::GetSampledKmerSet (lib/core/kmer_set_compact.h:120-203;
+ * dedup = 0: duplicates kept) and KmerSetCompact::ToKmerSet / GetKmerSetFromSPSS
+ * (lib/core/spss.h:1861-1941; dedup = 1: hash-set semantics). text = the strings
+ * concatenated (A/C/G/T only), str_offs: int64[n_strings + 1]. Only k-mers whose
+ * bucket lies in [bucket_lo, bucket_hi) are kept (0, 2^N = all): a rank's shard. */
+int kmsc_set_from_spss(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text,
+                       const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
+                       int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
+
+/* ---- P3: all-pairs intersection counts ------------------------------------------ */
+/* Replaces GetEdgeWeight and the initial all-pairs loop of KmerSetSet's
+ * constructor (lib/core/kmer_set_set.h:158-219): out[i*n + j] =
+ * sum over b in bucket_ids of |merge-count(S_i[b], S_j[b])| (int64), for ALL i, j
+ * (symmetric; the diagonal holds each set's key count over those buckets).
+ * bucket_ids == NULL: all 2^N buckets (exact matrix); otherwise the reference's
+ * sampled list (any order; an id listed twice counts once, as its map does,
+ * :127-131). out is host memory (n*n int64). key_visits (may be NULL) receives
+ * sum_{i<j} sum_b (len_i[b] + len_j[b]) -- the work the reference's merge does. */
+int kmsc_pair_counts(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                     const int32_t* bucket_ids, int32_t n_ids, int64_t* out, int64_t* key_visits);
+/* Same, result left in DEVICE memory d_out (n*n int64, on the context's stream):
+ * the per-rank partial a caller all-reduces (NCCL) across a prefix-sharded job. */
+int kmsc_pair_counts_device(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                            const int32_t* bucket_ids, int32_t n_ids, int64_t* d_out);
+/* Row mode (lib/core/kmer_set_set.h:385-425, the 3n-2 re-weights after a merge):
+ * out[r*n + l] = weight(rows[r], l) for l in [0, n). */
+int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                          const int32_t* rows, int32_t n_rows, const int32_t* bucket_ids,
+                          int32_t n_ids, int64_t* out);
+
+/* ---- P4: pair split / set algebra ------------------------------------------------ */
+/* Replaces kmer_set_set.h:332-343: n = Intersection(j, k); j.Sub(n); k.Sub(n)
+ * (lib/core/kmer_set.h:177-187, 301-305) in one pass over both CSRs. Any output
+ * pointer may be NULL. Inputs must be duplicate-free (true sets). */
+int kmsc_pair_split(kmsc_ctx* ctx, const kmsc_set* j, const kmsc_set* k, kmsc_set** inter,
+                    kmsc_set** j_minus, kmsc_set** k_minus);
+/* KmerSet::Add(other) (lib/core/kmer_set.h:164-174) over m sets: the union that
+ * KmerSetSet::Get / KmerSetSetReader::Get build (kmer_set_set.h:433-454, 672-755). */
+int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_set** out);
+/* KmerSet::Diff (lib/core/kmer_set.h:191-214): |a \ b| + |b \ a|. */
+int kmsc_set_diff(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, int64_t* diff);
+
+/* ---- P1: k-mer counting with cutoff ------------------------------------------------ */
+/* Replaces KmerCounter::FromFASTA/FromReads + ToKmerSet
+ * (lib/core/kmer_counter.h:64-133, 161-243). fasta = the file bytes (strict
+ * 2-line records, '\n' separated). Validation as :163-203: returns KMSC_E_FORMAT
+ * with the reference's message. Counts saturate at 255; k-mers with
+ * count < cutoff are dropped and counted in *cutoff_count. counts_out (may be
+ * NULL) receives a malloc'd uint8 array aligned with the set's key order
+ * (free with kmsc_free_host). */
+int kmsc_count_fasta(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* fasta, int64_t n_bytes,
+                     int canonical, int cutoff, kmsc_set** out, int64_t* cutoff_count,
+                     int64_t* n_distinct);
+/* Same from reads (one per line, no headers; FromReads semantics). */
+int kmsc_count_reads(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* reads, int64_t n_bytes,
+                     int canonical, int cutoff, kmsc_set** out, int64_t* cutoff_count,
+                     int64_t* n_distinct);
+/* KmerCounter::Get (lib/core/kmer_counter.h:246-254) after a counting call with
+ * keep_counts: count of one k-mer value in the last counted set of this context. */
+int kmsc_count_get(kmsc_ctx* ctx, uint64_t kmer, int* count);
+
+/* ---- P5: dense-bitmap Gram for K <= 15 ---------------------------------------------- */
+/* out[i*n + j] = |S_i & S_j| over 2^(2K)-bit bitmaps (exact all-bucket matrix);
+ * same result as kmsc_pair_counts(bucket_ids = NULL) for duplicate-free sets. */
+int kmsc_bitmap_gram(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n, int64_t* out);
+
+/* ---- P6: bucket payload codec (delta + streamvbyte-style 0124) ------------------------ */
+/* Internal container (the reference has no on-disk binary format to match:
+ * SURVEY.md section 0). encode: device set -> malloc'd host bytes; decode: back. */
+int kmsc_codec_encode(kmsc_ctx* ctx, const kmsc_set* set, uint8_t** bytes, int64_t* n_bytes);
+int kmsc_codec_decode(kmsc_ctx* ctx, const uint8_t* bytes, int64_t n_bytes, kmsc_set** out);
+void kmsc_free_host(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMSC_H_ */

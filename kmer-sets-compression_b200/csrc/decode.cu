@@ -1,0 +1,112 @@
+// decode.cu -- P2: SPSS text -> device CSR set.
+//
+// Replaces KmerSetCompact::GetSampledKmerSet (reference
+// lib/core/kmer_set_compact.h:120-203: every position of every string -> k-mer ->
+// canonical -> (bucket, key), kept if the bucket is selected, each bucket sorted)
+// and KmerSetCompact::ToKmerSet / GetKmerSetFromSPSS (lib/core/spss.h:1861-1941,
+// the same decode into hash sets). The reference re-materialises ASCII strings
+// and builds each k-mer from a fresh substr (kmer.h:22-46); here the text is
+// packed once to 2 bits per base (the KmerSetCompact layout, kmer_set_compact.h:
+// 206-255, first base in the top bits) and every position extracts its k-mer
+// with two 64-bit loads.
+#include "kmer_pipeline.cuh"
+
+namespace kmsc {
+namespace {
+
+// thread per 32 bases: ASCII -> one 64-bit word of 2-bit codes; flags bad characters
+__global__ void pack_ascii_kernel(const unsigned char* __restrict__ text, unsigned long long n,
+                                  unsigned long long* __restrict__ words, unsigned long long n_words,
+                                  int* __restrict__ bad_char) {
+  const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  unsigned long long out = 0;
+  const unsigned long long base = w * 32;
+  int bad = 0;
+#pragma unroll 8
+  for (int j = 0; j < 32; j++) {
+    const unsigned long long p = base + j;
+    unsigned c = 0;
+    if (p < n) {
+      const unsigned ch = text[p];
+      // A 0x41, C 0x43, G 0x47, T 0x54: (ch >> 1) & 3 = 0, 1, 3, 2; fix the G/T swap
+      c = (ch >> 1) & 3u;
+      c ^= c >> 1;
+      bad |= !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T');
+    }
+    out = (out << 2) | c;
+  }
+  words[w] = out;
+  if (bad) atomicExch(bad_char, 1);
+}
+
+// thread per string: no k-mer starts in the last K-1 positions of a string
+// (kmer_set_compact.h:149: j < length - K + 1)
+__global__ void mark_string_tails_kernel(const long long* __restrict__ str_offs, long long n_strings, int K,
+                                         uint32_t* __restrict__ bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_strings) return;
+  const long long b = str_offs[i], e = str_offs[i + 1];
+  long long a = e - (K - 1);
+  if (a < b) a = b;
+  for (long long p = a; p < e; p++) atomicOr(&bad[p >> 5], 1u << (p & 31));
+}
+
+}  // namespace
+}  // namespace kmsc
+
+using namespace kmsc;
+
+extern "C" int kmsc_set_from_spss(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text,
+                                  const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
+                                  int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out) {
+  if (!ctx || !out || !str_offs || n_strings < 0) { set_error("bad argument"); return KMSC_E_INVALID; }
+  if (K < 1 || K > 32 || N < 0 || N > 2 * K || 2 * K - N > 8 * key_bytes) { set_error("bad K/N/key_bytes"); return KMSC_E_INVALID; }
+  if (bucket_lo < 0 || bucket_hi > (1 << N) || bucket_lo > bucket_hi) { set_error("bad bucket range"); return KMSC_E_INVALID; }
+  if (str_offs[0] != 0) { set_error("str_offs[0] must be 0"); return KMSC_E_INVALID; }
+  for (int64_t i = 0; i < n_strings; i++)
+    if (str_offs[i + 1] < str_offs[i]) { set_error("str_offs not monotone at %lld", (long long)i); return KMSC_E_INVALID; }
+  const int64_t n = str_offs[n_strings];
+  if (n > 0 && !text) { set_error("text is NULL"); return KMSC_E_INVALID; }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+
+  // device staging: text | str_offs | words | bad bits | flag   (ctx->work3 is free until the pipeline's mode>0 sort)
+  const size_t n_words = (size_t)(n + 31) / 32 + 2;
+  const size_t n_badw = (size_t)(n + 31) / 32 + 2;
+  size_t off = 0;
+  const size_t o_text = off; off += ((size_t)n + 255) & ~(size_t)255;
+  const size_t o_offs = off; off += (((size_t)n_strings + 1) * 8 + 255) & ~(size_t)255;
+  const size_t o_words = off; off += (n_words * 8 + 255) & ~(size_t)255;
+  const size_t o_bad = off; off += (n_badw * 4 + 255) & ~(size_t)255;
+  const size_t o_flag = off; off += 256;
+  KMSC_TRY(ctx->stage.reserve(off));
+  unsigned char* base = (unsigned char*)ctx->stage.p;
+  unsigned char* d_text = base + o_text;
+  long long* d_offs = (long long*)(base + o_offs);
+  unsigned long long* d_words = (unsigned long long*)(base + o_words);
+  uint32_t* d_bad = (uint32_t*)(base + o_bad);
+  int* d_flag = (int*)(base + o_flag);
+
+  if (n > 0) KMSC_CUDA(cudaMemcpyAsync(d_text, text, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  KMSC_CUDA(cudaMemcpyAsync(d_offs, str_offs, ((size_t)n_strings + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  KMSC_CUDA(cudaMemsetAsync(d_bad, 0, n_badw * 4, ctx->stream));
+  KMSC_CUDA(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+  pack_ascii_kernel<<<(unsigned)((n_words + 127) / 128), 128, 0, ctx->stream>>>(d_text, (unsigned long long)n, d_words,
+                                                                              n_words, d_flag);
+  if (n_strings > 0)
+    mark_string_tails_kernel<<<(unsigned)((n_strings + 127) / 128), 128, 0, ctx->stream>>>(d_offs, n_strings, K, d_bad);
+  count_launch(ctx, 2);
+  KMSC_CUDA(cudaGetLastError());
+  void* pin = nullptr;
+  KMSC_TRY(ctx_pinned(ctx, 64, &pin));
+  KMSC_CUDA(cudaMemcpyAsync(pin, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (*(int*)pin) { set_error("SPSS text holds a character other than A, C, G, T"); return KMSC_E_FORMAT; }
+
+  PipelineInput in{d_words, d_bad, n};
+  PipelineOptions opt{K, N, key_bytes, canonical, bucket_lo, bucket_hi, dedup ? 1 : 0, 1};
+  PipelineResult res;
+  KMSC_TRY(run_kmer_pipeline(ctx, in, opt, &res));
+  *out = res.set;
+  return KMSC_OK;
+}

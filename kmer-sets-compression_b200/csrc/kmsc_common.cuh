@@ -1,0 +1,93 @@
+// kmsc_common.cuh -- shared declarations for libkmsc (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "kmsc.h"
+
+namespace kmsc {
+
+constexpr int kMaxFineLevel = 6;  // fine offsets exist for levels 0..kMaxFineLevel
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define KMSC_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return ::kmsc::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define KMSC_TRY(call)          \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != KMSC_OK) return rc__; \
+  } while (0)
+
+// grow-only device scratch buffer owned by a context
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+};
+
+}  // namespace kmsc
+
+struct kmsc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int64_t launches = 0;
+  kmsc::Scratch plan;     // pair_counts planning buffers
+  kmsc::Scratch work;     // generic per-call scratch
+  kmsc::Scratch work2;
+  kmsc::Scratch work3;
+  kmsc::Scratch stage;    // input staging (text, packed bases)
+  kmsc::Scratch small;    // small per-call device arrays (descriptors, ids)
+  void* pinned = nullptr; // pinned host staging
+  size_t pinned_cap = 0;
+  // pair_counts: redundancy (keys per distinct key in a tile) seen by the last call
+  double pc_rho = 0.0;
+  int pc_rho_n = 0, pc_rho_k = 0;
+  unsigned long long pc_last_stats[3] = {0, 0, 0};
+  unsigned long long pc_last_L = 0;
+  // last counting result (kmsc_count_get)
+  kmsc_set* last_counted = nullptr;
+  bool last_counted_owned = false;
+  uint8_t* last_counts = nullptr;  // device, aligned with last_counted keys
+};
+
+// Device-resident bucketed set (CSR). keys are ascending inside each bucket.
+// lev[f] (f = 0..max_level) are fine offsets: lev[f][x] for x in [0, 2^(N+f)]
+// is the index of the first key whose (bucket << f | top f bits of key) >= x;
+// lev[0] is the bucket-level CSR offs array.
+struct kmsc_set {
+  int K = 0, N = 0, key_bytes = 0;
+  int key_bits = 0;       // 2K - N
+  int max_level = 0;      // min(kMaxFineLevel, key_bits)
+  int64_t n_keys = 0;
+  void* keys = nullptr;   // device, n_keys * key_bytes (+ padding)
+  uint32_t* lev_base = nullptr;  // device, all levels in one allocation
+  uint32_t* lev[kmsc::kMaxFineLevel + 1] = {};
+  int has_dups = -1;      // -1 unknown, 0 no, 1 yes
+};
+
+namespace kmsc {
+
+int ctx_pinned(kmsc_ctx* ctx, size_t bytes, void** out);
+inline void count_launch(kmsc_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+// set construction helpers (set_build.cu)
+int set_alloc(kmsc_ctx* ctx, int K, int N, int key_bytes, int64_t n_keys, kmsc_set** out);
+// fills lev[1..max_level] from keys + lev[0]; also sets has_dups
+int set_build_levels(kmsc_ctx* ctx, kmsc_set* s);
+// given lev[max_level] (finest) already filled, derive coarser levels by striding
+int set_derive_levels(kmsc_ctx* ctx, kmsc_set* s);
+int set_check_dups(kmsc_ctx* ctx, kmsc_set* s);
+
+}  // namespace kmsc

@@ -1,0 +1,237 @@
+// set_ops.cu -- P4: set algebra on device CSR sets.
+//
+// Replaces the split step of KmerSetSet's main loop (reference
+// lib/core/kmer_set_set.h:332-343: n = Intersection(j, k); j.Sub(n); k.Sub(n),
+// built from KmerSet::Sub / Intersection, lib/core/kmer_set.h:177-187, 301-305),
+// KmerSet::Add(other) (:164-174) and KmerSet::Diff (:191-214). The reference
+// decodes two SPSS into hash sets and erases key by key; here both inputs are
+// sorted CSR, so one merge per finest-level fine bucket classifies every key as
+// common / only-in-A / only-in-B. Pass 1 counts per fine bucket, a device scan
+// turns the counts into the outputs' finest-level offsets (which are kept: they
+// ARE the outputs' fine index), pass 2 writes the keys. Inputs must be
+// duplicate-free (true sets).
+//
+// Algorithmic bytes: (n_j + n_k + |n| + |j\n| + |k\n|) * sizeof(Key)
+// + 5 * (2^N + 1) * 4.
+#include "kmsc_common.cuh"
+#include "scan.cuh"
+
+namespace kmsc {
+
+// one thread per finest-level fine bucket: two-pointer classification
+template <typename KeyT, bool WRITE>
+__global__ void merge_classify_kernel(const KeyT* __restrict__ ka, const uint32_t* __restrict__ la,
+                                      const KeyT* __restrict__ kb, const uint32_t* __restrict__ lb,
+                                      uint32_t NF,
+                                      uint32_t* __restrict__ cI, uint32_t* __restrict__ cA,
+                                      uint32_t* __restrict__ cB,   // counts (pass 1) / offsets (pass 2)
+                                      KeyT* __restrict__ oI, KeyT* __restrict__ oA, KeyT* __restrict__ oB,
+                                      KeyT* __restrict__ oU, const uint32_t* __restrict__ offU) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= NF) return;
+  uint32_t i = la[x], ie = la[x + 1], j = lb[x], je = lb[x + 1];
+  uint32_t nI = 0, nA = 0, nB = 0;
+  uint32_t pI = 0, pA = 0, pB = 0, pU = 0;
+  if (WRITE) {
+    if (oI) pI = cI[x];
+    if (oA) pA = cA[x];
+    if (oB) pB = cB[x];
+    if (oU) pU = offU[x];
+  }
+  while (i < ie && j < je) {
+    const KeyT a = ka[i], b = kb[j];
+    if (a < b) {
+      if (WRITE) { if (oA) oA[pA++] = a; if (oU) oU[pU++] = a; } else nA++;
+      i++;
+    } else if (b < a) {
+      if (WRITE) { if (oB) oB[pB++] = b; if (oU) oU[pU++] = b; } else nB++;
+      j++;
+    } else {
+      if (WRITE) { if (oI) oI[pI++] = a; if (oU) oU[pU++] = a; } else nI++;
+      i++; j++;
+    }
+  }
+  if (WRITE) {
+    for (; i < ie; i++) { const KeyT a = ka[i]; if (oA) oA[pA++] = a; if (oU) oU[pU++] = a; }
+    for (; j < je; j++) { const KeyT b = kb[j]; if (oB) oB[pB++] = b; if (oU) oU[pU++] = b; }
+  } else {
+    nA += ie - i;
+    nB += je - j;
+    cI[x] = nI; cA[x] = nA; cB[x] = nB;
+  }
+}
+
+__global__ void add3_kernel(const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t* out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i] + c[i];
+}
+
+struct MergePlan {
+  uint32_t NF;
+  int F;
+  uint32_t *cI, *cA, *cB, *cU, *bsum, *totals;  // device
+};
+
+static int check_pair(const kmsc_set* a, const kmsc_set* b) {
+  if (!a || !b) { set_error("NULL set"); return KMSC_E_INVALID; }
+  if (a->K != b->K || a->N != b->N || a->key_bytes != b->key_bytes) {
+    set_error("sets have different (K,N,KeyType)");
+    return KMSC_E_INVALID;
+  }
+  return KMSC_OK;
+}
+
+template <typename KeyT>
+static void launch_classify(kmsc_ctx* ctx, bool write, const kmsc_set* a, const kmsc_set* b, const MergePlan& mp,
+                            void* oI, void* oA, void* oB, void* oU) {
+  const int threads = 128;
+  const unsigned blocks = (mp.NF + threads - 1) / threads;
+  if (write)
+    merge_classify_kernel<KeyT, true><<<blocks, threads, 0, ctx->stream>>>(
+        (const KeyT*)a->keys, a->lev[mp.F], (const KeyT*)b->keys, b->lev[mp.F], mp.NF, mp.cI, mp.cA, mp.cB,
+        (KeyT*)oI, (KeyT*)oA, (KeyT*)oB, (KeyT*)oU, mp.cU);
+  else
+    merge_classify_kernel<KeyT, false><<<blocks, threads, 0, ctx->stream>>>(
+        (const KeyT*)a->keys, a->lev[mp.F], (const KeyT*)b->keys, b->lev[mp.F], mp.NF, mp.cI, mp.cA, mp.cB,
+        nullptr, nullptr, nullptr, nullptr, nullptr);
+  count_launch(ctx);
+}
+
+static void dispatch_classify(kmsc_ctx* ctx, bool write, const kmsc_set* a, const kmsc_set* b, const MergePlan& mp,
+                              void* oI, void* oA, void* oB, void* oU) {
+  switch (a->key_bytes) {
+    case 2: launch_classify<uint16_t>(ctx, write, a, b, mp, oI, oA, oB, oU); break;
+    case 4: launch_classify<uint32_t>(ctx, write, a, b, mp, oI, oA, oB, oU); break;
+    default: launch_classify<unsigned long long>(ctx, write, a, b, mp, oI, oA, oB, oU); break;
+  }
+}
+
+// pass 1 + scans; host_totals = {|A&B|, |A\B|, |B\A|}
+static int merge_count(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, MergePlan* mp, bool want_union,
+                       uint32_t host_totals[3]) {
+  mp->F = a->max_level;
+  mp->NF = (uint32_t)1 << (a->N + mp->F);
+  const size_t ent = (size_t)mp->NF + 1;
+  const size_t sb = scan_scratch_entries(mp->NF);
+  KMSC_TRY(ctx->work2.reserve((ent * 4 + sb + 16) * 4));
+  uint32_t* p = (uint32_t*)ctx->work2.p;
+  mp->cI = p; p += ent;
+  mp->cA = p; p += ent;
+  mp->cB = p; p += ent;
+  mp->cU = p; p += ent;
+  mp->bsum = p; p += sb;
+  mp->totals = p;
+  dispatch_classify(ctx, false, a, b, *mp, nullptr, nullptr, nullptr, nullptr);
+  KMSC_CUDA(cudaGetLastError());
+  if (want_union) {
+    add3_kernel<<<(mp->NF + 255) / 256, 256, 0, ctx->stream>>>(mp->cI, mp->cA, mp->cB, mp->cU, mp->NF);
+    count_launch(ctx);
+    KMSC_TRY(exclusive_scan_u32(ctx, mp->cU, mp->cU, mp->NF, mp->bsum, mp->totals + 3));
+  }
+  KMSC_TRY(exclusive_scan_u32(ctx, mp->cI, mp->cI, mp->NF, mp->bsum, mp->totals + 0));
+  KMSC_TRY(exclusive_scan_u32(ctx, mp->cA, mp->cA, mp->NF, mp->bsum, mp->totals + 1));
+  KMSC_TRY(exclusive_scan_u32(ctx, mp->cB, mp->cB, mp->NF, mp->bsum, mp->totals + 2));
+  void* pin = nullptr;
+  KMSC_TRY(ctx_pinned(ctx, 64, &pin));
+  KMSC_CUDA(cudaMemcpyAsync(pin, mp->totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(host_totals, pin, 12);
+  return KMSC_OK;
+}
+
+// new set whose finest-level offsets are d_offs (NF + 1 entries)
+static int set_from_fine_offsets(kmsc_ctx* ctx, const kmsc_set* like, int64_t n_keys, const uint32_t* d_offs,
+                                 uint32_t NF, kmsc_set** out) {
+  kmsc_set* s = nullptr;
+  KMSC_TRY(set_alloc(ctx, like->K, like->N, like->key_bytes, n_keys, &s));
+  cudaError_t e = cudaMemcpyAsync(s->lev[s->max_level], d_offs, ((size_t)NF + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) { kmsc_set_free(ctx, s); return cuda_fail(e, "copy offsets", __FILE__, __LINE__); }
+  int rc = set_derive_levels(ctx, s);
+  if (rc != KMSC_OK) { kmsc_set_free(ctx, s); return rc; }
+  s->has_dups = 0;
+  *out = s;
+  return KMSC_OK;
+}
+
+}  // namespace kmsc
+
+using namespace kmsc;
+
+extern "C" {
+
+int kmsc_pair_split(kmsc_ctx* ctx, const kmsc_set* j, const kmsc_set* k, kmsc_set** inter,
+                    kmsc_set** j_minus, kmsc_set** k_minus) {
+  if (!ctx) { set_error("ctx is NULL"); return KMSC_E_INVALID; }
+  KMSC_TRY(check_pair(j, k));
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  MergePlan mp;
+  uint32_t tot[3];
+  KMSC_TRY(merge_count(ctx, j, k, &mp, false, tot));
+  kmsc_set *sI = nullptr, *sA = nullptr, *sB = nullptr;
+  int rc = KMSC_OK;
+  if (inter) rc = set_from_fine_offsets(ctx, j, tot[0], mp.cI, mp.NF, &sI);
+  if (rc == KMSC_OK && j_minus) rc = set_from_fine_offsets(ctx, j, tot[1], mp.cA, mp.NF, &sA);
+  if (rc == KMSC_OK && k_minus) rc = set_from_fine_offsets(ctx, j, tot[2], mp.cB, mp.NF, &sB);
+  if (rc == KMSC_OK) {
+    dispatch_classify(ctx, true, j, k, mp, sI ? sI->keys : nullptr, sA ? sA->keys : nullptr,
+                      sB ? sB->keys : nullptr, nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "pair_split write", __FILE__, __LINE__);
+  }
+  if (rc != KMSC_OK) {
+    kmsc_set_free(ctx, sI); kmsc_set_free(ctx, sA); kmsc_set_free(ctx, sB);
+    return rc;
+  }
+  if (inter) *inter = sI;
+  if (j_minus) *j_minus = sA;
+  if (k_minus) *k_minus = sB;
+  return KMSC_OK;
+}
+
+int kmsc_set_diff(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, int64_t* diff) {
+  if (!ctx || !diff) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  KMSC_TRY(check_pair(a, b));
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  MergePlan mp;
+  uint32_t tot[3];
+  KMSC_TRY(merge_count(ctx, a, b, &mp, false, tot));
+  *diff = (int64_t)tot[1] + (int64_t)tot[2];
+  return KMSC_OK;
+}
+
+int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_set** out) {
+  if (!ctx || !sets || m < 1 || !out) { set_error("bad argument"); return KMSC_E_INVALID; }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  // left fold of two-way unions; intermediates are freed as we go
+  kmsc_set* acc = nullptr;
+  for (int32_t t = 0; t < m; t++) {
+    const kmsc_set* b = sets[t];
+    if (!b) { set_error("sets[%d] is NULL", t); kmsc_set_free(ctx, acc); return KMSC_E_INVALID; }
+    const kmsc_set* a = acc ? acc : sets[0];
+    if (t == 0 && m > 1) continue;
+    int rc = check_pair(a, b);
+    MergePlan mp;
+    uint32_t tot[3];
+    if (rc == KMSC_OK) rc = merge_count(ctx, a, b, &mp, true, tot);
+    kmsc_set* u = nullptr;
+    if (rc == KMSC_OK) {
+      const int64_t nu = (m == 1) ? a->n_keys : (int64_t)tot[0] + tot[1] + tot[2];
+      rc = set_from_fine_offsets(ctx, a, nu, mp.cU, mp.NF, &u);
+    }
+    if (rc == KMSC_OK) {
+      dispatch_classify(ctx, true, a, b, mp, nullptr, nullptr, nullptr, u->keys);
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "set_union write", __FILE__, __LINE__);
+    }
+    kmsc_set_free(ctx, acc);
+    acc = nullptr;
+    if (rc != KMSC_OK) { kmsc_set_free(ctx, u); return rc; }
+    acc = u;
+  }
+  *out = acc;
+  return KMSC_OK;
+}
+
+}  // extern "C"

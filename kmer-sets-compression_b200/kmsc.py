@@ -1,0 +1,295 @@
+"""ctypes binding of libkmsc (include/kmsc.h) -- the thin Python face of the C ABI.
+
+Used by tests/ and bench.py. It holds no algorithm: every call goes straight into
+the CUDA library and raises if the library or a GPU is missing (no CPU fallback).
+Class and method names follow the reference's (KmerSet, KmerSetCompact.GetSampledKmerSet,
+KmerSetSet's GetEdgeWeight ...), see include/kmsc.h for the file:line each replaces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libkmsc.so"
+
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+
+KEY_DTYPES = {2: np.uint16, 4: np.uint32, 8: np.uint64}
+
+EXPORTS = [
+    "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
+    "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
+    "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
+    "kmsc_set_from_spss", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
+    "kmsc_pair_split", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
+    "kmsc_count_get", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
+]
+
+
+class KmscError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile libkmsc.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-s", "-j8", "-C", str(PKG_DIR / "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise KmscError("building libkmsc.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise KmscError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    L.kmsc_last_error.restype = C.c_char_p
+    L.kmsc_version.restype = C.c_char_p
+    L.kmsc_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.kmsc_ctx_destroy.argtypes = [C.c_void_p]
+    L.kmsc_ctx_destroy.restype = None
+    L.kmsc_ctx_sync.argtypes = [C.c_void_p]
+    L.kmsc_ctx_stream.argtypes = [C.c_void_p]
+    L.kmsc_ctx_stream.restype = C.c_void_p
+    L.kmsc_ctx_launch_count.argtypes = [C.c_void_p]
+    L.kmsc_ctx_launch_count.restype = C.c_int64
+    L.kmsc_set_from_csr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i64p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.kmsc_set_from_kmers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _u64p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.kmsc_set_to_csr.argtypes = [C.c_void_p, C.c_void_p, _i64p, C.c_void_p]
+    L.kmsc_set_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.kmsc_set_free.restype = None
+    L.kmsc_set_size.argtypes = [C.c_void_p, C.c_void_p, _i64p]
+    L.kmsc_set_hash.argtypes = [C.c_void_p, C.c_void_p, _u64p]
+    L.kmsc_set_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _i64p]
+    L.kmsc_set_from_spss.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, _i64p, C.c_int64,
+                                     C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.kmsc_pair_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i64p, _i64p]
+    L.kmsc_pair_counts_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, C.c_void_p]
+    L.kmsc_pair_counts_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i32p,
+                                        C.c_int32, _i64p]
+    L.kmsc_pair_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.kmsc_set_union.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
+    L.kmsc_set_diff.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
+    L.kmsc_count_fasta.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                   C.POINTER(C.c_void_p), _i64p, _i64p]
+    L.kmsc_count_reads.argtypes = L.kmsc_count_fasta.argtypes
+    L.kmsc_count_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    L.kmsc_bitmap_gram.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i64p]
+    L.kmsc_codec_encode.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+    L.kmsc_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.kmsc_free_host.argtypes = [C.c_void_p]
+    L.kmsc_free_host.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise KmscError(f"libkmsc error {rc}: {lib().kmsc_last_error().decode()}")
+
+
+class DeviceSet:
+    """Device-resident KmerSet<K,N,KeyType> in CSR form (owned handle)."""
+
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.h = ctx, handle
+        K, N, kb, n = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        _check(lib().kmsc_set_info(handle, C.byref(K), C.byref(N), C.byref(kb), C.byref(n)))
+        self.K, self.N, self.key_bytes, self.n_keys = K.value, N.value, kb.value, n.value
+
+    def Size(self) -> int:  # KmerSet::Size
+        v = C.c_int64()
+        _check(lib().kmsc_set_size(self.ctx.h, self.h, C.byref(v)))
+        return v.value
+
+    def Hash(self) -> int:  # KmerSet::Hash
+        v = C.c_uint64()
+        _check(lib().kmsc_set_hash(self.ctx.h, self.h, C.byref(v)))
+        return v.value
+
+    def to_csr(self):
+        offs = np.zeros((1 << self.N) + 1, np.int64)
+        keys = np.zeros(max(1, self.n_keys), KEY_DTYPES[self.key_bytes])
+        _check(lib().kmsc_set_to_csr(self.ctx.h, self.h, offs.ctypes.data_as(_i64p), keys.ctypes.data))
+        return offs, keys[: self.n_keys]
+
+    def to_kmers(self) -> np.ndarray:
+        """ascending 2K-bit k-mer values (what KmerSet::Find returns, sorted)."""
+        offs, keys = self.to_csr()
+        buckets = np.repeat(np.arange(1 << self.N, dtype=np.uint64), np.diff(offs))
+        return (buckets << np.uint64(2 * self.K - self.N)) | keys.astype(np.uint64)
+
+    def free(self):
+        if self.h:
+            lib().kmsc_set_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU + one stream (kmsc_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        _check(lib().kmsc_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h.value
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().kmsc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self): _check(lib().kmsc_ctx_sync(self.h))
+    def launch_count(self) -> int: return lib().kmsc_ctx_launch_count(self.h)
+    def stream(self) -> int: return lib().kmsc_ctx_stream(self.h) or 0
+
+    # -- sets -----------------------------------------------------------------
+    def set_from_csr(self, K, N, key_bytes, offs, keys) -> DeviceSet:
+        offs = np.ascontiguousarray(offs, np.int64)
+        keys = np.ascontiguousarray(keys, KEY_DTYPES[key_bytes])
+        h = C.c_void_p()
+        _check(lib().kmsc_set_from_csr(self.h, K, N, key_bytes, offs.ctypes.data_as(_i64p), keys.ctypes.data, C.byref(h)))
+        return DeviceSet(self, h.value)
+
+    def set_from_kmers(self, K, N, key_bytes, kmers) -> DeviceSet:
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        h = C.c_void_p()
+        _check(lib().kmsc_set_from_kmers(self.h, K, N, key_bytes, kmers.ctypes.data_as(_u64p), len(kmers), C.byref(h)))
+        return DeviceSet(self, h.value)
+
+    def set_from_spss(self, K, N, key_bytes, strings, canonical=True, dedup=True, bucket_lo=0, bucket_hi=None,
+                      text=None, str_offs=None) -> DeviceSet:
+        """KmerSetCompact::ToKmerSet (dedup) / GetSampledKmerSet over a bucket range (dedup=False)."""
+        if text is None:
+            bs = [s.encode() if isinstance(s, str) else s for s in strings]
+            str_offs = np.zeros(len(bs) + 1, np.int64)
+            np.cumsum([len(b) for b in bs], out=str_offs[1:])
+            text = np.frombuffer(b"".join(bs), np.uint8) if bs else np.zeros(0, np.uint8)
+        text = np.ascontiguousarray(text, np.uint8)
+        str_offs = np.ascontiguousarray(str_offs, np.int64)
+        h = C.c_void_p()
+        hi = (1 << N) if bucket_hi is None else bucket_hi
+        _check(lib().kmsc_set_from_spss(self.h, K, N, key_bytes, text.ctypes.data, str_offs.ctypes.data_as(_i64p),
+                                        len(str_offs) - 1, int(canonical), int(dedup), bucket_lo, hi, C.byref(h)))
+        return DeviceSet(self, h.value)
+
+    # -- P3 -----------------------------------------------------------------------
+    def _handles(self, sets):
+        return (C.c_void_p * len(sets))(*[s.h for s in sets])
+
+    def pair_counts(self, sets, bucket_ids=None, with_visits=False):
+        n = len(sets)
+        out = np.zeros((n, n), np.int64)
+        visits = C.c_int64()
+        if bucket_ids is None:
+            idp, nid = None, 0
+        else:
+            ids = np.ascontiguousarray(bucket_ids, np.int32)
+            idp, nid = ids.ctypes.data_as(_i32p), len(ids)
+        _check(lib().kmsc_pair_counts(self.h, self._handles(sets), n, idp, nid, out.ctypes.data_as(_i64p), C.byref(visits)))
+        return (out, visits.value) if with_visits else out
+
+    def pair_counts_device(self, sets, d_out_ptr: int, bucket_ids=None):
+        n = len(sets)
+        if bucket_ids is None:
+            idp, nid = None, 0
+        else:
+            ids = np.ascontiguousarray(bucket_ids, np.int32)
+            idp, nid = ids.ctypes.data_as(_i32p), len(ids)
+        _check(lib().kmsc_pair_counts_device(self.h, self._handles(sets), n, idp, nid, C.c_void_p(d_out_ptr)))
+
+    def pair_counts_rows(self, sets, rows, bucket_ids=None):
+        n = len(sets)
+        rows = np.ascontiguousarray(rows, np.int32)
+        out = np.zeros((len(rows), n), np.int64)
+        if bucket_ids is None:
+            idp, nid = None, 0
+        else:
+            ids = np.ascontiguousarray(bucket_ids, np.int32)
+            idp, nid = ids.ctypes.data_as(_i32p), len(ids)
+        _check(lib().kmsc_pair_counts_rows(self.h, self._handles(sets), n, rows.ctypes.data_as(_i32p), len(rows),
+                                           idp, nid, out.ctypes.data_as(_i64p)))
+        return out
+
+    # -- P4 -------------------------------------------------------------------------
+    def pair_split(self, j: DeviceSet, k: DeviceSet):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().kmsc_pair_split(self.h, j.h, k.h, C.byref(a), C.byref(b), C.byref(c)))
+        return DeviceSet(self, a.value), DeviceSet(self, b.value), DeviceSet(self, c.value)
+
+    def set_union(self, sets) -> DeviceSet:
+        h = C.c_void_p()
+        _check(lib().kmsc_set_union(self.h, self._handles(sets), len(sets), C.byref(h)))
+        return DeviceSet(self, h.value)
+
+    def set_diff(self, a: DeviceSet, b: DeviceSet) -> int:
+        v = C.c_int64()
+        _check(lib().kmsc_set_diff(self.h, a.h, b.h, C.byref(v)))
+        return v.value
+
+    # -- P1 ---------------------------------------------------------------------------
+    def _count(self, fn, K, N, key_bytes, data: bytes, canonical, cutoff):
+        buf = np.frombuffer(data, np.uint8)
+        h = C.c_void_p()
+        cut, nd = C.c_int64(), C.c_int64()
+        _check(fn(self.h, K, N, key_bytes, buf.ctypes.data, len(buf), int(canonical), int(cutoff), C.byref(h),
+                  C.byref(cut), C.byref(nd)))
+        return DeviceSet(self, h.value), cut.value, nd.value
+
+    def count_fasta(self, K, N, key_bytes, data: bytes, canonical=True, cutoff=1):
+        return self._count(lib().kmsc_count_fasta, K, N, key_bytes, data, canonical, cutoff)
+
+    def count_reads(self, K, N, key_bytes, data: bytes, canonical=True, cutoff=1):
+        return self._count(lib().kmsc_count_reads, K, N, key_bytes, data, canonical, cutoff)
+
+    def count_get(self, kmer: int) -> int:
+        v = C.c_int()
+        _check(lib().kmsc_count_get(self.h, kmer, C.byref(v)))
+        return v.value
+
+    # -- P5 / P6 ------------------------------------------------------------------------
+    def bitmap_gram(self, sets):
+        n = len(sets)
+        out = np.zeros((n, n), np.int64)
+        _check(lib().kmsc_bitmap_gram(self.h, self._handles(sets), n, out.ctypes.data_as(_i64p)))
+        return out
+
+    def codec_encode(self, s: DeviceSet) -> bytes:
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().kmsc_codec_encode(self.h, s.h, C.byref(p), C.byref(n)))
+        data = C.string_at(p, n.value)
+        lib().kmsc_free_host(p)
+        return data
+
+    def codec_decode(self, data: bytes) -> DeviceSet:
+        buf = np.frombuffer(data, np.uint8)
+        h = C.c_void_p()
+        _check(lib().kmsc_codec_decode(self.h, buf.ctypes.data, len(buf), C.byref(h)))
+        return DeviceSet(self, h.value)

@@ -380,8 +380,13 @@ int64_t kmsc_o_edge_weight(const int64_t* offs_i, const void* keys_i,
                            int64_t* key_visits) {
   int64_t count = 0, visits = 0; /* lib/core/kmer_set_set.h:158-184 */
   const int32_t nb = bucket_ids ? n_ids : n_buckets;
+  /* a bucket id listed twice fills only ONE position of the sampled set
+   * (map[bucket_ids[i]] = i, kmer_set_compact.h:127-131; the other position stays
+   * empty), so it is merged once */
+  uint8_t* seen = bucket_ids ? (uint8_t*)calloc((size_t)n_buckets, 1) : NULL;
   for (int32_t t = 0; t < nb; t++) {
     const int32_t b = bucket_ids ? bucket_ids[t] : t;
+    if (seen) { if (seen[b]) continue; seen[b] = 1; }
     const int64_t ai = offs_i[b], na = offs_i[b + 1] - ai;
     const int64_t bj = offs_j[b], nbk = offs_j[b + 1] - bj;
     visits += na + nbk;
@@ -391,6 +396,7 @@ int64_t kmsc_o_edge_weight(const int64_t* offs_i, const void* keys_i,
       default: count += kmsc_o_merge_count((const uint64_t*)keys_i + ai, na, (const uint64_t*)keys_j + bj, nbk); break;
     }
   }
+  free(seen);
   if (key_visits) *key_visits = visits;
   return count;
 }

@@ -86,3 +86,23 @@ def test_reference_spss_is_valid(oracle, ref):
     assert weight == sum(len(s) for s in spss)
     allk = oracle.spss_kmers(spss, K, True)
     assert len(allk) == len(kmers) and np.array_equal(np.sort(allk), kmers)
+
+
+def test_repeated_bucket_ids_count_once(oracle, ref):
+    """a bucket id listed twice fills one position only (kmer_set_compact.h:127-131), so the
+    reference's position-wise merge (kmer_set_set.h:161-181) sees it once"""
+    cfg = 2
+    K, N, kb = CONFIGS[cfg]
+    rng = np.random.default_rng(9)
+    a = [_randseq(rng, 3000)]
+    b = [a[0][:1500] + _randseq(rng, 1500)]
+    ids = np.array([5, 7, 100, 5, 9000, 7], np.int32)
+    ids = np.concatenate([ids, rng.permutation(1 << N)[:400].astype(np.int32)])
+    ao, ak, _, _ = ref.sampled_set(cfg, a, True, ids)
+    bo, bk, _, _ = ref.sampled_set(cfg, b, True, ids)
+    want = sum(oracle.merge_count(ak[ao[i]:ao[i + 1]], bk[bo[i]:bo[i + 1]]) for i in range(len(ids)))
+    ka, kb_ = oracle.set_from_spss(a, K, True), oracle.set_from_spss(b, K, True)
+    oa, keysa = oracle.to_csr(ka, K, N, 2)
+    ob, keysb = oracle.to_csr(kb_, K, N, 2)
+    w, _ = oracle.pair_counts([oa, ob], [keysa, keysb], 2, 1 << N, bucket_ids=ids)
+    assert w[0, 1] == want
