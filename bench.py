@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json):
+pairwise k-mer intersections per second, as key-visits/s, where
+
+    key-visits = sum_{i<j} sum_{b in B} (len_i[b] + len_j[b])
+
+is the work the reference's GetEdgeWeight merge performs for the same matrix
+(lib/core/kmer_set_set.h:158-219).
+
+Workload at N=1 = BASELINE configs[1] ("C2"): 64 sets x 10M canonical 23-mers
+(<23,14,uint32>), sets derived from one random genome by a binary phylogeny of
+0.2 % substitutions, exact all-bucket N x N matrix. With N>1 ranks the k-mer prefix
+space is sharded by cumulative key count, every rank holds all 64 sets restricted
+to its prefix range and the genome grows with N so the per-GPU key count stays
+fixed ("weak" scaling); the partial matrices are summed by one NCCL all-reduce.
+
+  value  : key-visits/s with the CSR sets resident in HBM (P3 plan + main kernel
+           [+ all-reduce]), CUDA events on the launching stream, max over ranks.
+  e2e    : same metric through the C ABI from HOST buffers: per step the 2-bit
+           packed SPSS of every set (what KmerSetCompact holds in memory) is
+           copied from pinned host memory, decoded to CSR on the device (P2), the
+           matrix computed (P3) and read back.
+  --impl reference : the reference's own unmodified headers (oracle/_ref) running
+           KmerSetSet's constructor up to "calculated initial weights"
+           (GetSampledKmerSet per set + the all-pairs GetEdgeWeight loop over its
+           own 2 % bucket sample) on a bounded number of sets, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "kmer-sets-compression_b200"))
+sys.path.insert(0, str(ROOT / "tests"))
+
+K, N, KB = 23, 14, 4
+METRIC = "pairwise k-mer intersection throughput (key-visits/s = sum over pairs and buckets of len_i + len_j)"
+UNIT = "key-visits/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sets", type=int, default=64)
+    ap.add_argument("--kmers", type=int, default=10_000_000, help="k-mers per set per GPU")
+    ap.add_argument("--p", type=float, default=0.002)
+    ap.add_argument("--ref-sets", type=int, default=0, help="sets in the reference sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# synthetic data (torch on the GPU for speed; numpy fallback for the CPU arm)
+# ----------------------------------------------------------------------------
+
+def gen_sequences_torch(n_sets, G, p, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(12345)
+    seqs = [torch.randint(0, 4, (G,), dtype=torch.uint8, device=device, generator=g)]
+    for i in range(1, n_sets):
+        g.manual_seed(1000 + i)
+        par = seqs[(i - 1) // 2]
+        m = torch.rand(G, device=device, generator=g) < p
+        d = torch.randint(1, 4, (G,), dtype=torch.uint8, device=device, generator=g)
+        seqs.append(torch.where(m, (par + d) & 3, par))
+    return seqs
+
+
+def pack_torch(codes):
+    """codes uint8 (0..3) -> int64 words, 32 bases per word, first base in the top bits"""
+    import torch
+    G = codes.numel()
+    nw = (G + 31) // 32
+    pad = torch.zeros(nw * 32, dtype=torch.int64, device=codes.device)
+    pad[:G] = codes.to(torch.int64)
+    shifts = (62 - 2 * torch.arange(32, device=codes.device, dtype=torch.int64))
+    words = (pad.view(nw, 32) << shifts).sum(dim=1)
+    return torch.cat([words, torch.zeros(2, dtype=torch.int64, device=codes.device)])
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ----------------------------------------------------------------------------
+
+def reference_run(n_sets_sample, G, p, steps, warmup, n_workers):
+    """Times the reference's own constructor phases on `n_sets_sample` sets of the workload."""
+    import synth
+    from _oracle import Ref, set_ref_seed
+    set_ref_seed(4242)
+    ref = Ref()
+    ref.lib.ref_set_log_level(4)
+    seqs = synth.phylogeny_sequences(n_sets_sample, G, p)
+    tmp = tempfile.mkdtemp(prefix="kmsc_ref_")
+    files, lens = [], []
+    for i, s in enumerate(seqs):
+        f = os.path.join(tmp, f"{i}.txt")
+        with open(f, "wb") as fh:
+            for piece in synth.split_strings(s, K, 100000):  # an SPSS-like multi-string file
+                fh.write(piece + b"\n")
+        files.append(f)
+        km = synth.kmers_of(s, K, True)  # duplicates kept, like GetSampledKmerSet
+        lens.append(np.bincount((km >> np.uint64(2 * K - N)).astype(np.int64), minlength=1 << N))
+    lens = np.stack(lens)
+    times, visits = [], []
+    for it in range(warmup + steps):
+        c0 = ref.seed_counter()
+        out = ref.kmer_set_set(4, files, True, n_workers=n_workers, stop_after_weights=True)
+        assert out["rc"] == 1, out["rc"]
+        ids = ref.random_ints(c0, (1 << N) // 50, 0, (1 << N) - 1)
+        v = (n_sets_sample - 1) * int(lens[:, ids].sum())
+        if it >= warmup:
+            times.append(out["phase_s"][0] + out["phase_s"][1])
+            visits.append(v)
+    for f in files:
+        os.remove(f)
+    os.rmdir(tmp)
+    return sum(visits) / sum(times), float(np.mean(times)), times
+
+
+def port_run(n_sets_sample, G, p, n_threads):
+    """fallback CPU baseline: the oracle's merge loop (kmsc_oracle.c) on all buckets"""
+    import synth
+    from _oracle import Oracle
+    o = Oracle()
+    seqs = synth.phylogeny_sequences(n_sets_sample, G, p)
+    offs_l, keys_l = [], []
+    for s in seqs:
+        offs, keys = synth.csr_of(synth.kmer_set_of(s, K), K, N, KB)
+        offs_l.append(offs)
+        keys_l.append(keys)
+    t = time.time()
+    _, v = o.pair_counts(offs_l, keys_l, KB, 1 << N, n_threads=n_threads)
+    dt = time.time() - t
+    return v / dt, dt
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    G = args.kmers + K - 1  # bases per set per GPU
+    cores = os.cpu_count() or 1
+    config = {"workload": f"C2: {args.sets} sets x {args.kmers} canonical {K}-mers per GPU (<{K},{N},uint32>), "
+                          f"binary phylogeny p={args.p}, all-pairs intersection matrix over all {1 << N} buckets (exact)",
+              "n_sets": args.sets, "kmers_per_set_per_gpu": args.kmers, "k": K, "bucket_bits": N,
+              "parallelism": f"prefix-sharded x{world}" if world > 1 else "single GPU",
+              "l2": "inputs (2.56 GB/GPU) exceed the 126 MB L2; no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from _oracle import Ref
+        n_s = args.ref_sets or (8 if args.steps + args.warmup <= 16 else 4 if args.steps + args.warmup <= 40 else 2)
+        n_s = min(n_s, args.sets)
+        if Ref.available():
+            val, mean_s, _ = reference_run(n_s, G, args.p, args.steps, args.warmup, cores)
+            kind = "reference"
+            sample = (f"first {n_s} of the {args.sets} sets; KmerSetSet constructor up to 'calculated initial weights' "
+                      f"(GetSampledKmerSet + all-pairs GetEdgeWeight) over the reference's own 2% bucket sample "
+                      f"({(1 << N) // 50} of {1 << N} buckets), n_workers={cores}")
+        else:
+            val, mean_s = port_run(n_s, G, args.p, cores)
+            kind = "port"
+            sample = f"first {n_s} sets, all buckets, oracle merge loop, {cores} threads"
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    import kmsc
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    ctx = kmsc.Context(local_rank, stream.cuda_stream)
+
+    # data: genome grows with the number of ranks; every rank builds the same sequences
+    Gtot = args.kmers * world + K - 1
+    seqs = gen_sequences_torch(args.sets, Gtot, args.p, dev)
+    str_offs = np.array([0, Gtot], np.int64)
+    pinned, nbytes_in = [], 0
+    for s in seqs:
+        w = pack_torch(s)
+        h = torch.empty(w.numel(), dtype=torch.int64, pin_memory=True)
+        h.copy_(w)
+        pinned.append(h)
+        nbytes_in += (Gtot + 31) // 32 * 8 + str_offs.nbytes
+    del seqs
+    torch.cuda.synchronize()
+
+    # prefix shard by cumulative key count of set 0
+    lo, hi = 0, 1 << N
+    if world > 1:
+        s0 = ctx.set_from_packed(K, N, KB, None, str_offs, words_ptr=pinned[0].data_ptr())
+        offs, _ = s0.to_csr()
+        s0.free()
+        cuts = [int(np.searchsorted(offs, offs[-1] * r / world)) for r in range(world + 1)]
+        cuts[0], cuts[-1] = 0, 1 << N
+        lo, hi = cuts[rank], cuts[rank + 1]
+
+    def build_sets():
+        return [ctx.set_from_packed(K, N, KB, None, str_offs, bucket_lo=lo, bucket_hi=hi, words_ptr=h.data_ptr())
+                for h in pinned]
+
+    sets = build_sets()
+    n = len(sets)
+    d_out = torch.zeros(n * n, dtype=torch.int64, device=dev)
+    keys_local = sum(s.n_keys for s in sets)
+    visits_local = (n - 1) * keys_local
+
+    def step_resident():
+        ctx.pair_counts_device(sets, d_out.data_ptr())
+        if world > 1:
+            dist.all_reduce(d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_ms, plan_ms, algo_bytes, main_launches = 0.0, 0.0, 0.0, 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        st = ctx.pair_counts_stats()
+        main_ms += st["main_ms"]; plan_ms += st["plan_ms"]; algo_bytes += st["algo_bytes"]
+        main_launches += int(st["main_launches"])
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, float(visits_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, visits_total = float(tm[0]), float(ts[1])
+    else:
+        visits_total = float(visits_local)
+    value = visits_total * args.steps / (ms / 1e3)
+    W = d_out.cpu().numpy().reshape(n, n)
+
+    # ---- e2e: host packed SPSS -> device CSR -> matrix -> host ------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(2, min(args.steps, 5))
+        host_out = np.zeros((n, n), np.int64)
+
+        def step_e2e():
+            ss = build_sets()
+            ctx.pair_counts_device(ss, d_out.data_ptr())
+            if world > 1:
+                dist.all_reduce(d_out)
+            host_out[:] = d_out.cpu().numpy().reshape(n, n)
+            for s in ss:
+                s.free()
+
+        for s in sets:
+            s.free()
+        step_e2e()
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms_e], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_e = float(tt[0])
+        assert np.array_equal(host_out, W), "e2e matrix differs from the resident run"
+        e2e = {"value": visits_total * e2e_steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes_in),
+               "d2h_bytes_per_step": int(n * n * 8), "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    per_launch_ms = main_ms / max(1, main_launches)
+    achieved = (algo_bytes / max(1, main_launches)) / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "pair_counts_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": algo_bytes / max(1, main_launches),
+                "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": main_ms / ms if ms else None,
+                "plan_ms_per_step": plan_ms / args.steps}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from _oracle import Ref
+        try:
+            if Ref.available():
+                v, mean_s, _ = reference_run(4, G, args.p, 1, 0, cores)
+                cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                "sample": "first 4 of the sets; reference KmerSetSet constructor up to 'calculated "
+                                          f"initial weights' over its own 2% bucket sample, n_workers={cores}; "
+                                          f"{mean_s:.1f} s"}
+            else:
+                v, dt = port_run(8, G, args.p, cores)
+                cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"first 8 sets, all buckets, oracle merge loop; {dt:.1f} s"}
+        except Exception as ex:  # the baseline must never take the bench line down
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local)}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

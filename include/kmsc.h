@@ -88,6 +88,15 @@ int kmsc_set_from_spss(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* t
                        const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
                        int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
 
+/* Same decode from the 2-bit packed form KmerSetCompact keeps in memory
+ * (lib/core/kmer_set_compact.h:206-255, 338-347): words = 32 bases per uint64,
+ * first base in the top two bits, codes A=0 C=1 G=2 T=3 (the bit order inside
+ * std::vector<bool> is not observable, so the container is ours); str_offs in
+ * BASES. words must hold ceil(total_bases / 32) + 1 entries. */
+int kmsc_set_from_packed(kmsc_ctx* ctx, int K, int N, int key_bytes, const uint64_t* words,
+                         const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
+                         int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
+
 /* ---- P3: all-pairs intersection counts ------------------------------------------ */
 /* Replaces GetEdgeWeight and the initial all-pairs loop of KmerSetSet's
  * constructor (lib/core/kmer_set_set.h:158-219): out[i*n + j] =
@@ -108,6 +117,14 @@ int kmsc_pair_counts_device(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t 
 int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                           const int32_t* rows, int32_t n_rows, const int32_t* bucket_ids,
                           int32_t n_ids, int64_t* out);
+
+/* Device-side timing and tiling facts of the LAST kmsc_pair_counts* call, for
+ * bench.py's roofline: out[0] main-kernel ms (CUDA events on the context's
+ * stream, summed over the call's launches), out[1] planning-kernels ms, out[2]
+ * keys read, out[3] distinct keys seen, out[4] tiles re-run after a table
+ * overflow, out[5] tile target L, out[6] main-kernel launches, out[7] algorithmic
+ * bytes (keys * sizeof(KeyType) + offsets read + n*n*8). */
+int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8);
 
 /* ---- P4: pair split / set algebra ------------------------------------------------ */
 /* Replaces kmer_set_set.h:332-343: n = Intersection(j, k); j.Sub(n); k.Sub(n)

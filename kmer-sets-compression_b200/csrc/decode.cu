@@ -57,9 +57,28 @@ __global__ void mark_string_tails_kernel(const long long* __restrict__ str_offs,
 
 using namespace kmsc;
 
+static int spss_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, const uint64_t* packed,
+                       const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
+                       int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
+
 extern "C" int kmsc_set_from_spss(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text,
                                   const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
                                   int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out) {
+  return spss_common(ctx, K, N, key_bytes, text, nullptr, str_offs, n_strings, canonical, dedup, bucket_lo, bucket_hi, out);
+}
+
+extern "C" int kmsc_set_from_packed(kmsc_ctx* ctx, int K, int N, int key_bytes, const uint64_t* words,
+                                    const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
+                                    int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out) {
+  if (!words && str_offs && n_strings > 0 && str_offs[n_strings] > 0) { set_error("words is NULL"); return KMSC_E_INVALID; }
+  static const uint64_t zero[2] = {0, 0};
+  return spss_common(ctx, K, N, key_bytes, nullptr, words ? words : zero, str_offs, n_strings, canonical, dedup,
+                     bucket_lo, bucket_hi, out);
+}
+
+static int spss_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, const uint64_t* packed,
+                       const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
+                       int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out) {
   if (!ctx || !out || !str_offs || n_strings < 0) { set_error("bad argument"); return KMSC_E_INVALID; }
   if (K < 1 || K > 32 || N < 0 || N > 2 * K || 2 * K - N > 8 * key_bytes) { set_error("bad K/N/key_bytes"); return KMSC_E_INVALID; }
   if (bucket_lo < 0 || bucket_hi > (1 << N) || bucket_lo > bucket_hi) { set_error("bad bucket range"); return KMSC_E_INVALID; }
@@ -67,7 +86,7 @@ extern "C" int kmsc_set_from_spss(kmsc_ctx* ctx, int K, int N, int key_bytes, co
   for (int64_t i = 0; i < n_strings; i++)
     if (str_offs[i + 1] < str_offs[i]) { set_error("str_offs not monotone at %lld", (long long)i); return KMSC_E_INVALID; }
   const int64_t n = str_offs[n_strings];
-  if (n > 0 && !text) { set_error("text is NULL"); return KMSC_E_INVALID; }
+  if (n > 0 && !text && !packed) { set_error("text is NULL"); return KMSC_E_INVALID; }
   KMSC_CUDA(cudaSetDevice(ctx->device));
 
   // device staging: text | str_offs | words | bad bits | flag   (ctx->work3 is free until the pipeline's mode>0 sort)
@@ -87,12 +106,18 @@ extern "C" int kmsc_set_from_spss(kmsc_ctx* ctx, int K, int N, int key_bytes, co
   uint32_t* d_bad = (uint32_t*)(base + o_bad);
   int* d_flag = (int*)(base + o_flag);
 
-  if (n > 0) KMSC_CUDA(cudaMemcpyAsync(d_text, text, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if (packed) {
+    KMSC_CUDA(cudaMemcpyAsync(d_words, packed, ((size_t)(n + 31) / 32) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    KMSC_CUDA(cudaMemsetAsync(d_words + (n + 31) / 32, 0, 16, ctx->stream));
+  } else if (n > 0) {
+    KMSC_CUDA(cudaMemcpyAsync(d_text, text, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   KMSC_CUDA(cudaMemcpyAsync(d_offs, str_offs, ((size_t)n_strings + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   KMSC_CUDA(cudaMemsetAsync(d_bad, 0, n_badw * 4, ctx->stream));
   KMSC_CUDA(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
-  pack_ascii_kernel<<<(unsigned)((n_words + 127) / 128), 128, 0, ctx->stream>>>(d_text, (unsigned long long)n, d_words,
-                                                                              n_words, d_flag);
+  if (!packed)
+    pack_ascii_kernel<<<(unsigned)((n_words + 127) / 128), 128, 0, ctx->stream>>>(d_text, (unsigned long long)n, d_words,
+                                                                                n_words, d_flag);
   if (n_strings > 0)
     mark_string_tails_kernel<<<(unsigned)((n_strings + 127) / 128), 128, 0, ctx->stream>>>(d_offs, n_strings, K, d_bad);
   count_launch(ctx, 2);

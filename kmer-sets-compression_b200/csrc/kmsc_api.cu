@@ -46,6 +46,7 @@ void Scratch::release() {
 int ctx_pinned(kmsc_ctx* ctx, size_t bytes, void** out) {
   if (bytes > ctx->pinned_cap) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < 3; i++) if (ctx->pc_ev[i]) cudaEventDestroy(ctx->pc_ev[i]);
     ctx->pinned = nullptr;
     ctx->pinned_cap = 0;
     size_t want = bytes + bytes / 4 + 4096;

@@ -698,6 +698,9 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int mw,
     memcpy(pb, h_bitmap, sz_bitmap);
     KMSC_CUDA(cudaMemcpyAsync(d.bitmap, pb, sz_bitmap, cudaMemcpyHostToDevice, ctx->stream));
   }
+  for (int i = 0; i < 3; i++)
+    if (!ctx->pc_ev[i]) KMSC_CUDA(cudaEventCreate(&ctx->pc_ev[i]));
+  KMSC_CUDA(cudaEventRecord(ctx->pc_ev[0], ctx->stream));
   PlanParams pp;
   pp.NF = NF; pp.f = f; pp.n_sets = n; pp.L = L;
   {
@@ -720,6 +723,7 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int mw,
     count_launch(ctx, 4);
     KMSC_CUDA(cudaGetLastError());
   }
+  KMSC_CUDA(cudaEventRecord(ctx->pc_ev[1], ctx->stream));
   int rc;
   switch (s0->key_bytes) {
     case 2: rc = launch_main_mw<uint16_t>(ctx, mw, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
@@ -727,11 +731,23 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int mw,
     default: rc = launch_main_mw<unsigned long long>(ctx, mw, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
   }
   if (rc != KMSC_OK) return rc;
+  KMSC_CUDA(cudaEventRecord(ctx->pc_ev[2], ctx->stream));
   // stats come back through pinned memory; the sync also protects the staging buffer
   unsigned long long* h_stats = (unsigned long long*)((unsigned char*)pin + sz_desc + sz_bitmap);
   KMSC_CUDA(cudaMemcpyAsync(h_stats, d.stats, 32, cudaMemcpyDeviceToHost, ctx->stream));
   KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 4; i++) host_stats[i] = h_stats[i];
+  {
+    float ms_plan = 0, ms_main = 0;
+    KMSC_CUDA(cudaEventElapsedTime(&ms_plan, ctx->pc_ev[0], ctx->pc_ev[1]));
+    KMSC_CUDA(cudaEventElapsedTime(&ms_main, ctx->pc_ev[1], ctx->pc_ev[2]));
+    ctx->pc_plan_ms += ms_plan;
+    ctx->pc_main_ms += ms_main;
+    ctx->pc_main_launches += 1;
+    // algorithmic bytes of this launch: every key once + the two offset rows per tile are
+    // folded into (NF+1)*n*4 offsets + the n*n*8 result
+    ctx->pc_algo_bytes += (double)h_stats[0] * s0->key_bytes + (double)(nb + 1) * n * 4.0;
+  }
   if (host_stats[3]) { set_error("pair_counts: a tile could not be split further (%llu failures)", host_stats[3]); return KMSC_E_STATE; }
   return KMSC_OK;
 }
@@ -757,6 +773,10 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
   }
   const int nb = 1 << s0->N;
   KMSC_CUDA(cudaSetDevice(ctx->device));
+  ctx->pc_main_ms = ctx->pc_plan_ms = 0;
+  ctx->pc_main_launches = 0;
+  ctx->pc_algo_bytes = (double)n * n * 8.0;
+  ctx->pc_last_stats[0] = ctx->pc_last_stats[1] = ctx->pc_last_stats[2] = 0;
   KMSC_CUDA(cudaMemsetAsync(d_W, 0, (size_t)n * n * 8, ctx->stream));
 
   // selection bitmap (host)
@@ -828,6 +848,7 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
     }
     KMSC_TRY(run_phase(ctx, sets, n, mw, probe.data(), L_cons, mean_bucket, d_W, st));
     if (st[1] > 0) rho = (double)st[0] / (double)st[1];
+    ctx->pc_last_stats[0] += st[0]; ctx->pc_last_stats[1] += st[1]; ctx->pc_last_stats[2] += st[2];
     phase2 = rest.data();
   }
   unsigned long long L = L_cons;
@@ -842,7 +863,7 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
     ctx->pc_rho_n = n;
     ctx->pc_rho_k = s0->K;
   }
-  ctx->pc_last_stats[0] = st[0]; ctx->pc_last_stats[1] = st[1]; ctx->pc_last_stats[2] = st[2];
+  ctx->pc_last_stats[0] += st[0]; ctx->pc_last_stats[1] += st[1]; ctx->pc_last_stats[2] += st[2];
   ctx->pc_last_L = L;
   return KMSC_OK;
 }
@@ -872,6 +893,15 @@ int kmsc_pair_counts(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
     for (int i = 0; i < n; i++) s += out[(size_t)i * n + i];
     *key_visits = (int64_t)(n - 1) * s;
   }
+  return KMSC_OK;
+}
+
+int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8) {
+  if (!ctx || !out8) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  out8[0] = ctx->pc_main_ms; out8[1] = ctx->pc_plan_ms;
+  out8[2] = (double)ctx->pc_last_stats[0]; out8[3] = (double)ctx->pc_last_stats[1];
+  out8[4] = (double)ctx->pc_last_stats[2]; out8[5] = (double)ctx->pc_last_L;
+  out8[6] = (double)ctx->pc_main_launches; out8[7] = ctx->pc_algo_bytes;
   return KMSC_OK;
 }
 

@@ -27,7 +27,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
 ]
@@ -77,6 +77,9 @@ def lib() -> C.CDLL:
     L.kmsc_set_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _i64p]
     L.kmsc_set_from_spss.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, _i64p, C.c_int64,
                                      C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.kmsc_set_from_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, _i64p, C.c_int64,
+                                       C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.kmsc_pair_counts_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.kmsc_pair_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i64p, _i64p]
     L.kmsc_pair_counts_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, C.c_void_p]
     L.kmsc_pair_counts_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i32p,
@@ -199,6 +202,26 @@ class Context:
         _check(lib().kmsc_set_from_spss(self.h, K, N, key_bytes, text.ctypes.data, str_offs.ctypes.data_as(_i64p),
                                         len(str_offs) - 1, int(canonical), int(dedup), bucket_lo, hi, C.byref(h)))
         return DeviceSet(self, h.value)
+
+    def set_from_packed(self, K, N, key_bytes, words, str_offs, canonical=True, dedup=True, bucket_lo=0,
+                        bucket_hi=None, words_ptr=None) -> DeviceSet:
+        """same decode from 2-bit packed bases (32 per uint64, first base in the top bits);
+        words_ptr: raw host pointer (e.g. a pinned torch tensor's data_ptr) instead of an array"""
+        str_offs = np.ascontiguousarray(str_offs, np.int64)
+        if words_ptr is None:
+            words = np.ascontiguousarray(words, np.uint64)
+            words_ptr = words.ctypes.data
+        h = C.c_void_p()
+        hi = (1 << N) if bucket_hi is None else bucket_hi
+        _check(lib().kmsc_set_from_packed(self.h, K, N, key_bytes, C.c_void_p(words_ptr), str_offs.ctypes.data_as(_i64p),
+                                          len(str_offs) - 1, int(canonical), int(dedup), bucket_lo, hi, C.byref(h)))
+        return DeviceSet(self, h.value)
+
+    def pair_counts_stats(self) -> dict:
+        out = (C.c_double * 8)()
+        _check(lib().kmsc_pair_counts_stats(self.h, out))
+        keys = ["main_ms", "plan_ms", "keys", "distinct", "retries", "L", "main_launches", "algo_bytes"]
+        return dict(zip(keys, list(out)))
 
     # -- P3 -----------------------------------------------------------------------
     def _handles(self, sets):

@@ -1,0 +1,102 @@
+"""P1 parity (GPU): kmsc_count_fasta / kmsc_count_reads / kmsc_count_get through the C ABI
+vs the oracle's restatement of KmerCounter (reference lib/core/kmer_counter.h:64-264) and
+the golden fixtures produced by the reference's own code."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "kmer-sets-compression_b200"))
+from _oracle import CONFIGS  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = json.loads((Path(__file__).parent / "golden" / "ref_golden.json").read_text())
+KB = {5: 2, 9: 2, 15: 2, 19: 4, 23: 4, 31: 8}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import kmsc
+    c = kmsc.Context(0)
+    yield c
+    c.close()
+
+
+def test_reference_known_answer(ctx, oracle):  # test/kmer_counter.cc:64-91
+    s, cut, nd = ctx.count_reads(5, 3, 2, b"AACCGTT\nAACCGTA\n", canonical=False, cutoff=1)
+    assert nd == 4 and cut == 0
+    for name, c in (("AACCG", 2), ("ACCGT", 2), ("CCGTT", 1), ("CCGTA", 1), ("AAAAA", 0)):
+        assert ctx.count_get(oracle.bits(name)) == c
+    s2, cut2, _ = ctx.count_reads(5, 3, 2, b"AACCGTT\nAACCGTA", canonical=False, cutoff=2)
+    assert cut2 == 2 and [oracle.string(int(k), 5) for k in s2.to_kmers()] == ["AACCG", "ACCGT"]
+
+
+def test_golden_counter(ctx):
+    for e in GOLD["counter"]:
+        K, N, _ = CONFIGS[e["cfg"]]
+        reads = GOLD["counter_reads"][e["reads_id"]]
+        data = "".join(r + "\n" for r in reads).encode()
+        s, cut, nd = ctx.count_reads(K, N, KB[K], data, canonical=e["canonical"], cutoff=e["cutoff"])
+        assert nd == len(e["kmers"]) and cut == e["cutoff_count"]
+        assert s.to_kmers().tolist() == e["kept"]
+        for k, c in list(zip(e["kmers"], e["counts"]))[:40]:
+            assert ctx.count_get(k) == c
+
+
+@pytest.mark.parametrize("K,N", [(15, 14), (23, 14), (31, 14), (19, 10)])
+@pytest.mark.parametrize("canonical", [True, False])
+def test_fasta_counts_vs_oracle(ctx, oracle, K, N, canonical):
+    rng = np.random.default_rng(K + 7)
+    base = "".join(rng.choice(list("ACGT"), 20000))
+    reads, lines = [], []
+    for i in range(3000):
+        a = int(rng.integers(0, 19800))
+        r = base[a:a + int(rng.integers(1, 200))]
+        if rng.random() < 0.1:
+            p = int(rng.integers(0, len(r)))
+            r = r[:p] + "N" + r[p + 1:]
+        reads.append(r)
+        lines += [f">r{i}", r]
+    reads.append("")
+    lines += [">empty", ""]
+    kmers, counts = oracle.count_reads(reads, K, canonical)
+    for cutoff in (1, 2, 4):
+        kept, cut = oracle.counter_to_set(kmers, counts, cutoff)
+        data = ("\n".join(lines) + "\n").encode()
+        s, gcut, nd = ctx.count_fasta(K, N, KB[K], data, canonical=canonical, cutoff=cutoff)
+        assert nd == len(kmers) and gcut == cut
+        assert np.array_equal(s.to_kmers(), kept)
+    idx = rng.integers(0, len(kmers), 30)
+    for i in idx:
+        assert ctx.count_get(int(kmers[i])) == int(counts[i])
+    # no trailing newline: same result (std::getline semantics, core/io.h:31-34)
+    s2, _, nd2 = ctx.count_fasta(K, N, KB[K], "\n".join(lines[:-2]).encode(), canonical=canonical, cutoff=1)
+    assert nd2 == len(kmers)
+
+
+def test_saturation_at_255(ctx, oracle):  # kmer_counter.h:28-38, test/kmer_counter.cc:12-16
+    data = ("ACGTA\n" * 300 + "CCCCC\n" * 255 + "GGGGG\n" * 254).encode()
+    s, cut, nd = ctx.count_reads(5, 3, 2, data, canonical=False, cutoff=255)
+    assert nd == 3 and cut == 1
+    assert ctx.count_get(oracle.bits("ACGTA")) == 255 and ctx.count_get(oracle.bits("GGGGG")) == 254
+    assert sorted(oracle.string(int(k), 5) for k in s.to_kmers()) == ["ACGTA", "CCCCC"]
+    # cutoff is a uint8 (kmer_counter.h:214): 256 wraps to 0 and keeps everything
+    s, cut, _ = ctx.count_reads(5, 3, 2, data, canonical=False, cutoff=256)
+    assert cut == 0 and s.Size() == 3
+
+
+def test_fasta_validation(ctx):
+    import kmsc
+    for e in GOLD["fasta"]:
+        data = "".join(l + "\n" for l in e["lines"]).encode()
+        if e["rc"] == 0:
+            s, cut, nd = ctx.count_fasta(5, 3, 2, data, canonical=True, cutoff=1)
+            assert nd == e["n_distinct"]
+        else:
+            with pytest.raises(kmsc.KmscError) as ei:
+                ctx.count_fasta(5, 3, 2, data, canonical=True, cutoff=1)
+            want = "even number of lines" if e["rc"] == 1 else "invalid FASTA file"
+            assert want in str(ei.value), (e["lines"], str(ei.value))
