@@ -248,62 +248,150 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   return x;
 }
 
+// Shared-memory layout with compile-time offsets (so every access keeps the
+// shared address space: LDS / STS / ATOMS, not generic LD / ST).
+template <typename TK, int MW>
+struct PcLayout {
+  using C = PcCfg<MW>;
+  static constexpr size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+  static constexpr int NPAD = 32 * MW;
+  static constexpr int NB4 = NPAD / 4;
+  static constexpr size_t o_keys = 0;
+  static constexpr size_t o_mask = a16((size_t)(C::S + 1) * sizeof(TK));
+  static constexpr size_t o_colT = a16(o_mask + (size_t)(C::S + 1) * MW * 4);
+  static constexpr size_t o_order = o_colT + (size_t)C::CW * NPAD * 4;
+  static constexpr size_t o_kp = a16(o_order + (size_t)(C::D + 1) * 2);
+  static constexpr size_t o_sbeg = o_kp + (size_t)NPAD * 8;
+  static constexpr size_t o_send = o_sbeg + (size_t)NPAD * 4;
+  static constexpr size_t o_segpre = o_send + (size_t)NPAD * 4;
+  static constexpr size_t o_misc = o_segpre + (size_t)NPAD * 4;
+  static constexpr size_t o_stack = o_misc + 64 * 4;
+  static constexpr size_t o_blk = o_stack + (size_t)kStackMax * 8;
+  static constexpr size_t total = a16(o_blk + (size_t)(NB4 * (NB4 + 1) / 2) * 2);
+};
+
+// misc[] slots
+constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscItems = 3, kMiscSp = 4, kMiscSpecial = 5,
+              kMiscWsum = 8;
+
+// Slow path of the table lookup: the first probe missed (empty slot, another key,
+// or the key equals the empty marker). Returns the slot of `key`, inserting it.
+template <typename TK, int S, int DMAX>
+__device__ __noinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int* misc, TK key, uint32_t h) {
+  const TK EMPTY = (TK)~(TK)0;
+  if (sizeof(TK) == 4 && key == EMPTY) {
+    // the one key that collides with the empty marker lives in the extra slot S
+    if (atomicExch(&misc[kMiscSpecial], 1) == 0) {
+      const int r = atomicAdd(&misc[kMiscNdist], 1);
+      if (r < DMAX) order[r] = (uint16_t)S; else misc[kMiscOverflow] = 1;
+    }
+    return S;
+  }
+  for (;;) {
+    const TK cur = skeys[h];
+    if (cur == key) return h;
+    if (cur == EMPTY) {
+      const TK old = atomicCAS(&skeys[h], EMPTY, key);
+      if (old == EMPTY) {
+        const int r = atomicAdd(&misc[kMiscNdist], 1);
+        if (r < DMAX) order[r] = (uint16_t)h; else misc[kMiscOverflow] = 1;
+        return h;
+      }
+      if (old == key) return h;
+    }
+    h = (h + 1) & (S - 1);
+  }
+}
+
+// Insert keys [beg, end) of set s (table key = top | key) and mark membership.
+// UNR keys per lane are handled as a batch: UNR independent global loads, UNR
+// independent first probes, then the (rare) slow paths, then UNR membership marks.
+// OWN: the mask byte (slot, s / 8) is only ever touched by the warp that owns set
+// group s / 8, and the keys of one set are distinct, so a plain byte
+// read-modify-write is race free (ordered across sets by __syncwarp). Otherwise a
+// shared-memory atomicOr on the mask word.
+template <typename KeyT, typename TK, int MW, bool OWN, int UNR>
+__device__ __forceinline__ void process_run(TK* skeys, uint32_t* smask, uint16_t* order, int* misc,
+                                            const KeyT* __restrict__ kp, uint32_t beg, uint32_t end, TK top,
+                                            int s, int lane, uint32_t cmask, uint32_t cp) {
+  using C = PcCfg<MW>;
+  const TK EMPTY = (TK)~(TK)0;
+  uint8_t* maskb = reinterpret_cast<uint8_t*>(smask);
+  for (uint32_t i0 = beg; i0 < end; i0 += 32 * UNR) {
+    KeyT kk[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const uint32_t i = i0 + u * 32 + lane;
+      kk[u] = (i < end) ? kp[i] : (KeyT)0;
+    }
+    TK key[UNR];
+    uint32_t h[UNR];
+    bool act[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const uint32_t i = i0 + u * 32 + lane;
+      key[u] = top | (TK)kk[u];
+      act[u] = (i < end) && (!cmask || (hash_class(key[u]) & cmask) == cp);
+      h[u] = hash_slot(key[u], C::LOG2S);
+    }
+    TK cur[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) cur[u] = skeys[h[u]];
+#pragma unroll
+    for (int u = 0; u < UNR; u++)
+      if (act[u] && (cur[u] != key[u] || (sizeof(TK) == 4 && key[u] == EMPTY)))
+        h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], h[u]);
+    if (OWN) {
+      uint8_t mv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) mv[u] = maskb[(size_t)h[u] * (MW * 4) + (s >> 3)];
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+        if (act[u]) maskb[(size_t)h[u] * (MW * 4) + (s >> 3)] = (uint8_t)(mv[u] | (1u << (s & 7)));
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+        if (act[u]) atomicOr(&smask[h[u] * MW + ((uint32_t)s >> 5)], 1u << (s & 31));
+    }
+    if (*(volatile int*)&misc[kMiscOverflow]) break;
+  }
+}
+
 template <int MW>
 struct PcSmem {
-  // dynamic shared memory carve-up (bytes), TK = table key type size
-  static __host__ __device__ size_t bytes(int tk_size) {
-    using C = PcCfg<MW>;
-    size_t b = 0;
-    b += (size_t)(C::S + 1) * tk_size;            // skeys
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)(C::S + 1) * MW * 4;             // smask
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)C::CW * 32 * MW * 4;             // colT
-    b += (size_t)(C::D + 1) * 2;                  // order (u16 slot ids)
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)32 * MW * 4 * 3;                 // sbeg, send, segpre
-    b += 64 * 4 + kStackMax * 8 + 64;             // misc + stack + alignment slack
-    b += (size_t)((32 * MW / 4) * (32 * MW / 4 + 1) / 2) * 2;  // block (bi,bj) table
-    return b;
+  static size_t bytes(int tk_size) {
+    return tk_size == 8 ? PcLayout<unsigned long long, MW>::total : PcLayout<uint32_t, MW>::total;
   }
 };
 
 template <typename KeyT, int MW>
-__global__ void __launch_bounds__(PcCfg<MW>::T)
+__global__ void __launch_bounds__(PcCfg<MW>::T, 1)
 pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t* __restrict__ offsT,
                    const Tile* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_p,
                    uint32_t* __restrict__ tile_counter, unsigned long long* __restrict__ W,
                    unsigned long long* __restrict__ stats, int key_bits, int fine_level) {
   using C = PcCfg<MW>;
   using TK = typename TableKey<KeyT>::type;
-  constexpr int S = C::S, DMAX = C::D, T = C::T, LOG2S = C::LOG2S, kChunkWords = C::CW;
+  using LY = PcLayout<TK, MW>;
+  constexpr int S = C::S, DMAX = C::D, T = C::T, kChunkWords = C::CW;
   constexpr int NPAD = 32 * MW;
   constexpr int NW = T / 32;
+  constexpr bool OWN = MW >= 2;   // byte-ownership membership marks (no shared atomics)
+  constexpr int UNR = 8;          // independent keys in flight per lane
   const TK EMPTY = (TK)~(TK)0;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char* sp = smem_raw;
-  TK* skeys = (TK*)sp; sp += (size_t)(S + 1) * sizeof(TK);
-  sp = (unsigned char*)(((uintptr_t)sp + 15) & ~(uintptr_t)15);
-  uint32_t* smask = (uint32_t*)sp; sp += (size_t)(S + 1) * MW * 4;
-  sp = (unsigned char*)(((uintptr_t)sp + 15) & ~(uintptr_t)15);
-  uint32_t* colT = (uint32_t*)sp; sp += (size_t)kChunkWords * NPAD * 4;
-  uint16_t* order = (uint16_t*)sp; sp += (size_t)(DMAX + 1) * 2;
-  sp = (unsigned char*)(((uintptr_t)sp + 15) & ~(uintptr_t)15);
-  uint32_t* sbeg = (uint32_t*)sp; sp += NPAD * 4;
-  uint32_t* send = (uint32_t*)sp; sp += NPAD * 4;
-  uint32_t* segpre = (uint32_t*)sp; sp += NPAD * 4;
-  int* misc = (int*)sp; sp += 64 * 4;
-  uint2* stack = (uint2*)sp; sp += kStackMax * 8;
-  uint8_t* blk_tab = (uint8_t*)sp;  // pairs (bi, bj)
-
-  int& s_ndist = misc[0];
-  int& s_overflow = misc[1];
-  int& s_tile = misc[2];
-  int& s_items = misc[3];
-  int& s_sp = misc[4];          // stack pointer
-  int& s_special = misc[5];     // special key seen in this pass
-  int* s_wsum = misc + 8;       // per-warp partial sums (<= 16)
+  TK* skeys = reinterpret_cast<TK*>(smem_raw + LY::o_keys);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + LY::o_mask);
+  uint32_t* colT = reinterpret_cast<uint32_t*>(smem_raw + LY::o_colT);
+  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + LY::o_order);
+  const void** skp = reinterpret_cast<const void**>(smem_raw + LY::o_kp);
+  uint32_t* sbeg = reinterpret_cast<uint32_t*>(smem_raw + LY::o_sbeg);
+  uint32_t* send = reinterpret_cast<uint32_t*>(smem_raw + LY::o_send);
+  uint32_t* segpre = reinterpret_cast<uint32_t*>(smem_raw + LY::o_segpre);
+  int* misc = reinterpret_cast<int*>(smem_raw + LY::o_misc);
+  uint2* stack = reinterpret_cast<uint2*>(smem_raw + LY::o_stack);
+  uint8_t* blk_tab = reinterpret_cast<uint8_t*>(smem_raw + LY::o_blk);  // pairs (bi, bj)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NB4 = (n_sets + 3) / 4;
@@ -314,11 +402,12 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
   // one-time init
   for (int i = tid; i <= S; i += T) skeys[i] = EMPTY;
   for (int i = tid; i < (S + 1) * MW; i += T) smask[i] = 0;
+  for (int i = tid; i < NPAD; i += T) skp[i] = i < n_sets ? sets[i].keys : nullptr;
   if (tid == 0) {
     int q = 0;
     for (int bi = 0; bi < NB4; bi++)
       for (int bj = bi; bj < NB4; bj++) { blk_tab[2 * q] = (uint8_t)bi; blk_tab[2 * q + 1] = (uint8_t)bj; q++; }
-    s_ndist = 0; s_overflow = 0; s_special = 0;
+    misc[kMiscNdist] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0;
   }
   __syncthreads();
 
@@ -336,9 +425,9 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
 
   const uint32_t n_tiles = *n_tiles_p;
   for (;;) {
-    if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
+    if (tid == 0) misc[kMiscTile] = (int)atomicAdd(tile_counter, 1u);
     __syncthreads();
-    const uint32_t t_id = (uint32_t)s_tile;
+    const uint32_t t_id = (uint32_t)misc[kMiscTile];
     if (t_id >= n_tiles) break;
     const Tile tl = tiles[t_id];
     const uint32_t bucket0 = tl.x0 >> fine_level;
@@ -353,9 +442,8 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
       sbeg[s] = b; send[s] = e;
     }
     __syncthreads();
-    // build work items: segments of kSeg keys; exclusive prefix over sets
-    {
-      // NPAD <= 256 <= T: thread s scans
+    if (!OWN) {
+      // build work items: segments of kSeg keys; exclusive prefix over sets (NPAD <= T)
       uint32_t nseg = 0;
       if (tid < NPAD) nseg = (send[tid] - sbeg[tid] + kSeg - 1) / kSeg;
       uint32_t inc = nseg;
@@ -363,88 +451,63 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      if (tid < NPAD && lane == 31) s_wsum[warp] = (int)inc;
+      if (tid < NPAD && lane == 31) misc[kMiscWsum + warp] = (int)inc;
       __syncthreads();
       uint32_t woff = 0;
       if (tid < NPAD)
-        for (int w = 0; w < warp; w++) woff += (uint32_t)s_wsum[w];
+        for (int w = 0; w < warp; w++) woff += (uint32_t)misc[kMiscWsum + w];
       if (tid < NPAD) segpre[tid] = woff + inc - nseg;
-      if (tid == NPAD - 1) s_items = (int)(woff + inc);
-      if (tid == 0) { s_sp = 1; stack[0] = make_uint2(0u, 1u); }  // class (p=0, P=1) = everything
+      if (tid == NPAD - 1) misc[kMiscItems] = (int)(woff + inc);
     }
+    if (tid == 0) { misc[kMiscSp] = 1; stack[0] = make_uint2(0u, 1u); }  // class (p=0, P=1) = everything
     __syncthreads();
-    const int n_items = s_items;
+    const int n_items = misc[kMiscItems];
 
     // process the stack of key classes (normally exactly one entry)
     for (;;) {
       __syncthreads();
-      if (s_sp == 0) break;
-      const uint2 cls = stack[s_sp - 1];
+      if (misc[kMiscSp] == 0) break;
+      const uint2 cls = stack[misc[kMiscSp] - 1];
       __syncthreads();
-      if (tid == 0) s_sp -= 1;
+      if (tid == 0) misc[kMiscSp] -= 1;
       const uint32_t cp = cls.x, cmask = cls.y - 1u;
 
       // ---- build -------------------------------------------------------
-      // insert one (composite) key of set s into the table and mark membership
-      auto insert_key = [&](TK key, uint32_t mword, uint32_t mbit) {
-        uint32_t h;
-        if (sizeof(TK) == 4 && key == EMPTY) {
-          h = S;  // the one key that collides with the empty marker lives in slot S
-          if (atomicExch(&s_special, 1) == 0) {
-            const int r = atomicAdd(&s_ndist, 1);
-            if (r < DMAX) order[r] = (uint16_t)S; else s_overflow = 1;
-          }
-        } else {
-          h = hash_slot(key, LOG2S);
-          for (;;) {
-            const TK cur = skeys[h];
-            if (cur == key) break;
-            if (cur == EMPTY) {
-              const TK old = atomicCAS(&skeys[h], EMPTY, key);
-              if (old == EMPTY) {
-                const int r = atomicAdd(&s_ndist, 1);
-                if (r < DMAX) order[r] = (uint16_t)h; else s_overflow = 1;
-                break;
+#define PROCESS_RUN(S_, BEG_, END_, TOP_) \
+  process_run<KeyT, TK, MW, OWN, UNR>(skeys, smask, order, misc, (const KeyT*)skp[S_], (BEG_), (END_), (TOP_), (S_), lane, cmask, cp)
+      if (OWN) {
+        // warp w owns set groups w, w + NW, ... (8 sets each)
+        const int n_groups = (n_sets + 7) >> 3;
+        for (int g = warp; g < n_groups; g += NW) {
+          const int s_end = min(n_sets, g * 8 + 8);
+          for (int s = g * 8; s < s_end; s++) {
+            if (nbk == 1) {
+              PROCESS_RUN(s, sbeg[s], send[s], (TK)0);
+            } else {
+              for (int b = 0; b < nbk; b++) {
+                const size_t row0 = (size_t)(bucket0 + (uint32_t)b) << fine_level;
+                const uint32_t beg = max(offsT[row0 * n_sets + s], sbeg[s]);
+                const uint32_t end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], send[s]);
+                PROCESS_RUN(s, beg, end, (TK)b << key_bits);
               }
-              if (old == key) break;
             }
-            h = (h + 1) & (S - 1);
+            __syncwarp();
+            if (*(volatile int*)&misc[kMiscOverflow]) break;
           }
+          if (*(volatile int*)&misc[kMiscOverflow]) break;
         }
-        atomicOr(&smask[h * MW + mword], mbit);
-      };
-      if (nbk == 1) {
-        // tile inside one bucket: the key alone identifies the k-mer
+      } else if (nbk == 1) {
+        // tile inside one bucket: the key alone identifies the k-mer; segments of kSeg keys
         for (int item = warp; item < n_items; item += NW) {
-          // set owning this item: largest s with segpre[s] <= item
-          int lo = 0, hi = NPAD - 1;
+          int lo = 0, hi = NPAD - 1;  // set owning this item: largest s with segpre[s] <= item
           while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (segpre[mid] <= (uint32_t)item) lo = mid; else hi = mid - 1;
           }
           const int s = lo;
           const uint32_t start = sbeg[s] + ((uint32_t)item - segpre[s]) * kSeg;
-          const uint32_t stop = min(start + (uint32_t)kSeg, send[s]);
-          const KeyT* __restrict__ kp = (const KeyT*)sets[s].keys;
-          const uint32_t mword = (uint32_t)s >> 5, mbit = 1u << (s & 31);
-          for (uint32_t i0 = start; i0 < stop; i0 += 128) {
-            KeyT kk[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const uint32_t i = i0 + u * 32 + lane;
-              kk[u] = (i < stop) ? kp[i] : (KeyT)0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const uint32_t i = i0 + u * 32 + lane;
-              if (i >= stop) continue;
-              const TK key = (TK)kk[u];
-              if (cmask && (hash_class(key) & cmask) != cp) continue;
-              insert_key(key, mword, mbit);
-            }
-            if (*(volatile int*)&s_overflow) break;
-          }
-          if (*(volatile int*)&s_overflow) break;
+          PROCESS_RUN(s, start, min(start + (uint32_t)kSeg, send[s]), (TK)0);
+          if (*(volatile int*)&misc[kMiscOverflow]) break;
         }
       } else {
         // tile spans several buckets: one item per (bucket, set); the table key is
@@ -453,47 +516,39 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
         for (int item = warp; item < n_bitems; item += NW) {
           const int b = item / n_sets, s = item - b * n_sets;
           const size_t row0 = (size_t)(bucket0 + (uint32_t)b) << fine_level;
-          uint32_t beg = offsT[row0 * n_sets + s];
-          uint32_t end = offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s];
-          beg = max(beg, sbeg[s]);
-          end = min(end, send[s]);
-          const KeyT* __restrict__ kp = (const KeyT*)sets[s].keys;
-          const uint32_t mword = (uint32_t)s >> 5, mbit = 1u << (s & 31);
-          const TK top = (TK)b << key_bits;
-          for (uint32_t i = beg + lane; i < end; i += 32) {
-            const TK key = top | (TK)kp[i];
-            if (cmask && (hash_class(key) & cmask) != cp) continue;
-            insert_key(key, mword, mbit);
-          }
-          if (*(volatile int*)&s_overflow) break;
+          const uint32_t beg = max(offsT[row0 * n_sets + s], sbeg[s]);
+          const uint32_t end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], send[s]);
+          PROCESS_RUN(s, beg, end, (TK)b << key_bits);
+          if (*(volatile int*)&misc[kMiscOverflow]) break;
         }
       }
+#undef PROCESS_RUN
       __syncthreads();
-      const int D = s_ndist;
-      if (s_overflow) {
+      const int D = misc[kMiscNdist];
+      if (misc[kMiscOverflow]) {
         // too many distinct keys for one pass: wipe the table, split the class in two
         __syncthreads();
         for (int i = tid; i <= S; i += T) skeys[i] = EMPTY;
         for (int i = tid; i < (S + 1) * MW; i += T) smask[i] = 0;
         if (tid == 0) {
-          s_ndist = 0; s_overflow = 0; s_special = 0;
+          misc[kMiscNdist] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0;
           const uint32_t P = cls.y;
-          if (s_sp + 2 <= kStackMax && P < 0x40000000u) {
-            stack[s_sp] = make_uint2(cp, P * 2);
-            stack[s_sp + 1] = make_uint2(cp + P, P * 2);
-            s_sp += 2;
+          if (misc[kMiscSp] + 2 <= kStackMax && P < 0x40000000u) {
+            stack[misc[kMiscSp]] = make_uint2(cp, P * 2);
+            stack[misc[kMiscSp] + 1] = make_uint2(cp + P, P * 2);
+            misc[kMiscSp] += 2;
           } else {
-            s_tile = -2;  // cannot split further: report failure
+            misc[kMiscTile] = -2;  // cannot split further: report failure
           }
         }
         st_over++;
         __syncthreads();
-        if (s_tile == -2) { if (tid == 0) atomicAdd(&stats[3], 1ull); break; }
+        if (misc[kMiscTile] == -2) { if (tid == 0) atomicAdd(&stats[3], 1ull); break; }
         continue;
       }
       st_dist += (tid == 0) ? (unsigned long long)D : 0ull;
 
-      // ---- gram, 1024 distinct keys per chunk ---------------------------
+      // ---- gram, CW * 32 distinct keys per chunk ---------------------------
       for (int c0 = 0; c0 < D; c0 += kChunkWords * 32) {
         const int ng = min(kChunkWords, (D - c0 + 31) >> 5);
         for (int g = warp; g < ng; g += NW) {
@@ -514,8 +569,8 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
 #pragma unroll
         for (int t = 0; t < NBLK; t++) {
           if (my_bi[t] < 0) continue;
-          const uint4* ca = (const uint4*)(colT + my_bi[t] * 4);
-          const uint4* cb = (const uint4*)(colT + my_bj[t] * 4);
+          const uint4* ca = reinterpret_cast<const uint4*>(colT + my_bi[t] * 4);
+          const uint4* cb = reinterpret_cast<const uint4*>(colT + my_bj[t] * 4);
           for (int g = 0; g < ng; g++) {
             const uint4 a = ca[g * (NPAD / 4)];
             const uint4 b = cb[g * (NPAD / 4)];
@@ -529,7 +584,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
         }
         __syncthreads();
       }
-      if (tid == 0) { s_ndist = 0; s_special = 0; }
+      if (tid == 0) { misc[kMiscNdist] = 0; misc[kMiscSpecial] = 0; }
     }
     if (tid < NPAD) st_keys += send[tid] - sbeg[tid];
     __syncthreads();
@@ -546,13 +601,9 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
         const int si = my_bi[t] * 4 + i, sj = my_bj[t] * 4 + j;
         const uint32_t v = acc[t][i * 4 + j];
         if (si >= n_sets || sj >= n_sets || v == 0) continue;
-        if (my_bi[t] == my_bj[t]) {
-          // diagonal block holds both (i,j) and (j,i): write each cell once
-          atomicAdd(&W[(size_t)si * n_sets + sj], (unsigned long long)v);
-        } else {
-          atomicAdd(&W[(size_t)si * n_sets + sj], (unsigned long long)v);
-          atomicAdd(&W[(size_t)sj * n_sets + si], (unsigned long long)v);
-        }
+        atomicAdd(&W[(size_t)si * n_sets + sj], (unsigned long long)v);
+        // a diagonal block holds both (i,j) and (j,i) already
+        if (my_bi[t] != my_bj[t]) atomicAdd(&W[(size_t)sj * n_sets + si], (unsigned long long)v);
       }
   }
   // stats: keys processed, distinct keys, overflow retries
