@@ -211,10 +211,18 @@ template <> struct TableKey<unsigned long long> { using type = unsigned long lon
 // per mask-width configuration: table slots, max distinct keys per pass, threads,
 // gram chunk in 32-key words. Sized so MW<=4 fits two CTAs per SM (228 KB).
 template <int MW> struct PcCfg;
-template <> struct PcCfg<1> { static constexpr int S = 8192, LOG2S = 13, D = 4096, T = 256, CW = 32; };
-template <> struct PcCfg<2> { static constexpr int S = 8192, LOG2S = 13, D = 3072, T = 256, CW = 16; };
-template <> struct PcCfg<4> { static constexpr int S = 4096, LOG2S = 12, D = 2048, T = 256, CW = 16; };
-template <> struct PcCfg<8> { static constexpr int S = 4096, LOG2S = 12, D = 2048, T = 512, CW = 16; };
+// UNR = keys in flight per lane, MINB = CTAs per SM the register budget is sized for.
+#ifndef PC_MW2_SMALL
+#define PC_MW2_SMALL 1
+#endif
+template <> struct PcCfg<1> { static constexpr int S = 8192, LOG2S = 13, D = 4096, T = 256, CW = 32, UNR = 8, MINB = 2; };
+#if PC_MW2_SMALL
+template <> struct PcCfg<2> { static constexpr int S = 4096, LOG2S = 12, D = 1536, T = 256, CW = 8, UNR = 4, MINB = 4; };
+#else
+template <> struct PcCfg<2> { static constexpr int S = 8192, LOG2S = 13, D = 3072, T = 256, CW = 16, UNR = 8, MINB = 2; };
+#endif
+template <> struct PcCfg<4> { static constexpr int S = 4096, LOG2S = 12, D = 2048, T = 256, CW = 16, UNR = 8, MINB = 1; };
+template <> struct PcCfg<8> { static constexpr int S = 4096, LOG2S = 12, D = 2048, T = 512, CW = 16, UNR = 4, MINB = 1; };
 
 constexpr int kSeg = 256;         // keys per build work item
 constexpr int kStackMax = 48;
@@ -304,57 +312,80 @@ __device__ __noinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int*
 }
 
 // Insert keys [beg, end) of set s (table key = top | key) and mark membership.
-// UNR keys per lane are handled as a batch: UNR independent global loads, UNR
-// independent first probes, then the (rare) slow paths, then UNR membership marks.
+// U keys per lane are handled as a batch: U independent global loads, U independent
+// first probes, then the (rare) slow paths, then U membership marks.
 // OWN: the mask byte (slot, s / 8) is only ever touched by the warp that owns set
 // group s / 8, and the keys of one set are distinct, so a plain byte
 // read-modify-write is race free (ordered across sets by __syncwarp). Otherwise a
 // shared-memory atomicOr on the mask word.
+template <typename KeyT, typename TK, int MW, bool OWN, int U, bool FULL>
+__device__ __forceinline__ void process_batch(TK* skeys, uint32_t* smask, uint16_t* order, int* misc,
+                                              const KeyT* __restrict__ kp, uint32_t i0, uint32_t end, TK top,
+                                              int s, int lane, uint32_t cmask, uint32_t cp) {
+  using C = PcCfg<MW>;
+  const TK EMPTY = (TK)~(TK)0;
+  uint8_t* maskb = reinterpret_cast<uint8_t*>(smask);
+  KeyT kk[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const uint32_t i = i0 + u * 32 + lane;
+    kk[u] = (FULL || i < end) ? __ldg(kp + i) : (KeyT)0;
+  }
+  TK key[U];
+  uint32_t h[U];
+  bool act[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const uint32_t i = i0 + u * 32 + lane;
+    key[u] = top | (TK)kk[u];
+    act[u] = (FULL || i < end) && (!cmask || (hash_class(key[u]) & cmask) == cp);
+    h[u] = hash_slot(key[u], C::LOG2S);
+  }
+  TK cur[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) cur[u] = skeys[h[u]];
+#pragma unroll
+  for (int u = 0; u < U; u++)
+    if (act[u] && (cur[u] != key[u] || (sizeof(TK) == 4 && key[u] == EMPTY)))
+      h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], h[u]);
+  if (OWN) {
+    uint8_t mv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) mv[u] = maskb[h[u] * (MW * 4) + (s >> 3)];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (act[u]) maskb[h[u] * (MW * 4) + (s >> 3)] = (uint8_t)(mv[u] | (1u << (s & 7)));
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (act[u]) atomicOr(&smask[h[u] * MW + ((uint32_t)s >> 5)], 1u << (s & 31));
+  }
+}
+
 template <typename KeyT, typename TK, int MW, bool OWN, int UNR>
 __device__ __forceinline__ void process_run(TK* skeys, uint32_t* smask, uint16_t* order, int* misc,
                                             const KeyT* __restrict__ kp, uint32_t beg, uint32_t end, TK top,
                                             int s, int lane, uint32_t cmask, uint32_t cp) {
-  using C = PcCfg<MW>;
-  const TK EMPTY = (TK)~(TK)0;
-  uint8_t* maskb = reinterpret_cast<uint8_t*>(smask);
-  for (uint32_t i0 = beg; i0 < end; i0 += 32 * UNR) {
-    KeyT kk[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const uint32_t i = i0 + u * 32 + lane;
-      kk[u] = (i < end) ? kp[i] : (KeyT)0;
-    }
-    TK key[UNR];
-    uint32_t h[UNR];
-    bool act[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const uint32_t i = i0 + u * 32 + lane;
-      key[u] = top | (TK)kk[u];
-      act[u] = (i < end) && (!cmask || (hash_class(key[u]) & cmask) == cp);
-      h[u] = hash_slot(key[u], C::LOG2S);
-    }
-    TK cur[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; u++) cur[u] = skeys[h[u]];
-#pragma unroll
-    for (int u = 0; u < UNR; u++)
-      if (act[u] && (cur[u] != key[u] || (sizeof(TK) == 4 && key[u] == EMPTY)))
-        h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], h[u]);
-    if (OWN) {
-      uint8_t mv[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; u++) mv[u] = maskb[(size_t)h[u] * (MW * 4) + (s >> 3)];
-#pragma unroll
-      for (int u = 0; u < UNR; u++)
-        if (act[u]) maskb[(size_t)h[u] * (MW * 4) + (s >> 3)] = (uint8_t)(mv[u] | (1u << (s & 7)));
-    } else {
-#pragma unroll
-      for (int u = 0; u < UNR; u++)
-        if (act[u]) atomicOr(&smask[h[u] * MW + ((uint32_t)s >> 5)], 1u << (s & 31));
-    }
-    if (*(volatile int*)&misc[kMiscOverflow]) break;
+  uint32_t i0 = beg;
+  // full batches: no bounds checks
+  for (; i0 + 32 * UNR <= end; i0 += 32 * UNR) {
+    process_batch<KeyT, TK, MW, OWN, UNR, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
+    if (*(volatile int*)&misc[kMiscOverflow]) return;
   }
+  // tail: rows of 32 keys in decreasing power-of-two batches
+  if (UNR >= 8 && i0 + 32 * 4 <= end) {
+    process_batch<KeyT, TK, MW, OWN, 4, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
+    i0 += 32 * 4;
+  }
+  if (UNR >= 4 && i0 + 32 * 2 <= end) {
+    process_batch<KeyT, TK, MW, OWN, 2, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
+    i0 += 32 * 2;
+  }
+  if (i0 + 32 <= end) {
+    process_batch<KeyT, TK, MW, OWN, 1, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
+    i0 += 32;
+  }
+  if (i0 < end) process_batch<KeyT, TK, MW, OWN, 1, false>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
 }
 
 template <int MW>
@@ -365,7 +396,7 @@ struct PcSmem {
 };
 
 template <typename KeyT, int MW>
-__global__ void __launch_bounds__(PcCfg<MW>::T, 1)
+__global__ void __launch_bounds__(PcCfg<MW>::T, PcCfg<MW>::MINB)
 pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t* __restrict__ offsT,
                    const Tile* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_p,
                    uint32_t* __restrict__ tile_counter, unsigned long long* __restrict__ W,
@@ -377,7 +408,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
   constexpr int NPAD = 32 * MW;
   constexpr int NW = T / 32;
   constexpr bool OWN = MW >= 2;   // byte-ownership membership marks (no shared atomics)
-  constexpr int UNR = 8;          // independent keys in flight per lane
+  constexpr int UNR = C::UNR;     // independent keys in flight per lane
   const TK EMPTY = (TK)~(TK)0;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
