@@ -282,10 +282,17 @@ struct PcLayout {
 constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscItems = 3, kMiscSp = 4, kMiscSpecial = 5,
               kMiscWsum = 8;
 
-// Slow path of the table lookup: the first probe missed (empty slot, another key,
-// or the key equals the empty marker). Returns the slot of `key`, inserting it.
+#ifndef PC_SLOW
+#define PC_SLOW 0      // 0 = divergent per-lane slow path, 1 = warp-convergent resolve_row
+#endif
+#ifndef PC_BUCKET2
+#define PC_BUCKET2 0   // 1 = two-slot buckets: the first probe reads slots h, h+1 with one 64-bit load
+#endif
+
+// Slow path, per lane (divergent): the first probe at slot h returned `c` != key.
+// An EMPTY first probe goes straight to the CAS; other keys probe linearly.
 template <typename TK, int S, int DMAX>
-__device__ __noinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int* misc, TK key, uint32_t h) {
+__device__ __forceinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int* misc, TK key, uint32_t h, TK c) {
   const TK EMPTY = (TK)~(TK)0;
   if (sizeof(TK) == 4 && key == EMPTY) {
     // the one key that collides with the empty marker lives in the extra slot S
@@ -296,9 +303,7 @@ __device__ __noinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int*
     return S;
   }
   for (;;) {
-    const TK cur = skeys[h];
-    if (cur == key) return h;
-    if (cur == EMPTY) {
+    if (c == EMPTY) {
       const TK old = atomicCAS(&skeys[h], EMPTY, key);
       if (old == EMPTY) {
         const int r = atomicAdd(&misc[kMiscNdist], 1);
@@ -308,7 +313,59 @@ __device__ __noinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int*
       if (old == key) return h;
     }
     h = (h + 1) & (S - 1);
+    c = skeys[h];
+    if (c == key) return h;
   }
+}
+
+// Slow path of the table lookup, warp-convergent: called by ALL 32 lanes of a warp
+// for one row of keys; lanes with `pend` set missed their first probe (empty slot,
+// another key, or the key equals the empty marker). Every iteration advances all
+// pending lanes by one probe; new keys get their rank in `order` through one
+// warp-aggregated shared atomic. Returns the slot of `key`.
+template <typename TK, int S, int DMAX>
+__device__ __forceinline__ uint32_t resolve_row(TK* skeys, uint16_t* order, int* misc, TK key, uint32_t h,
+                                               bool pend, int lane) {
+  const TK EMPTY = (TK)~(TK)0;
+  bool inserted = false;
+  if (sizeof(TK) == 4) {
+    // the one key that collides with the empty marker lives in the extra slot S
+    const bool sp = pend && key == EMPTY;
+    if (__any_sync(0xffffffffu, sp)) {
+      if (sp) {
+        h = S;
+        pend = false;
+        if (atomicExch(&misc[kMiscSpecial], 1) == 0) inserted = true;
+      }
+    }
+  }
+  while (__any_sync(0xffffffffu, pend)) {
+    if (pend) {
+      const TK c = skeys[h];
+      if (c == key) {
+        pend = false;
+      } else if (c == EMPTY) {
+        const TK old = atomicCAS(&skeys[h], EMPTY, key);
+        if (old == EMPTY) { inserted = true; pend = false; }
+        else if (old == key) pend = false;
+        else h = (h + 1) & (S - 1);
+      } else {
+        h = (h + 1) & (S - 1);
+      }
+    }
+  }
+  const unsigned im = __ballot_sync(0xffffffffu, inserted);
+  if (im) {
+    const int leader = __ffs(im) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&misc[kMiscNdist], __popc(im));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (inserted) {
+      const int r = base + __popc(im & ((1u << lane) - 1u));
+      if (r < DMAX) order[r] = (uint16_t)h; else misc[kMiscOverflow] = 1;
+    }
+  }
+  return h;
 }
 
 // Insert keys [beg, end) of set s (table key = top | key) and mark membership.
@@ -341,13 +398,48 @@ __device__ __forceinline__ void process_batch(TK* skeys, uint32_t* smask, uint16
     act[u] = (FULL || i < end) && (!cmask || (hash_class(key[u]) & cmask) == cp);
     h[u] = hash_slot(key[u], C::LOG2S);
   }
+#if PC_BUCKET2
+  // two-slot buckets: slots (h & ~1, h | 1) are read with one 64-bit load
+  TK c0[U], c1[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    h[u] &= ~1u;
+    if (sizeof(TK) == 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(&skeys[h[u]]);
+      c0[u] = (TK)v.x; c1[u] = (TK)v.y;
+    } else {
+      c0[u] = skeys[h[u]]; c1[u] = skeys[h[u] + 1];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const bool sp = sizeof(TK) == 4 && key[u] == EMPTY;
+    if (!sp && c1[u] == key[u]) { h[u] += 1; }
+    else if (sp || c0[u] != key[u]) {
+      if (act[u]) {
+        // first empty of the pair, else continue after the bucket
+        TK c = c0[u];
+        uint32_t hh = h[u];
+        if (c0[u] != EMPTY) { hh += 1; c = c1[u]; }
+        h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], hh, c);
+      }
+    }
+  }
+#else
   TK cur[U];
 #pragma unroll
   for (int u = 0; u < U; u++) cur[u] = skeys[h[u]];
 #pragma unroll
-  for (int u = 0; u < U; u++)
-    if (act[u] && (cur[u] != key[u] || (sizeof(TK) == 4 && key[u] == EMPTY)))
-      h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], h[u]);
+  for (int u = 0; u < U; u++) {
+    const bool pend = act[u] && (cur[u] != key[u] || (sizeof(TK) == 4 && key[u] == EMPTY));
+#if PC_SLOW == 1
+    if (__any_sync(0xffffffffu, pend))  // warp-uniform
+      h[u] = resolve_row<TK, C::S, C::D>(skeys, order, misc, key[u], h[u], pend, lane);
+#else
+    if (pend) h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], h[u], cur[u]);
+#endif
+  }
+#endif
   if (OWN) {
     uint8_t mv[U];
 #pragma unroll

@@ -13,8 +13,11 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libkmsc.so"
+# KMSC_LIB selects an experimental build of the same library (tools/build_variants.sh)
+LIB_PATH = Path(os.environ["KMSC_LIB"]) if os.environ.get("KMSC_LIB") else PKG_DIR / "libkmsc.so"
 
 _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
