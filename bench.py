@@ -238,7 +238,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream shared by torch (events, NCCL ordering, copies) and
+    # libkmsc, so CUDA events time the launching stream and collectives are ordered with it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = kmsc.Context(local_rank, stream.cuda_stream)
 
     # data: genome grows with the number of ranks; every rank builds the same sequences

@@ -156,6 +156,9 @@ int kmsc_count_reads(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* rea
 /* KmerCounter::Get (lib/core/kmer_counter.h:246-254) after a counting call with
  * keep_counts: count of one k-mer value in the last counted set of this context. */
 int kmsc_count_get(kmsc_ctx* ctx, uint64_t kmer, int* count);
+/* uint8 counts of the last counting call, aligned with the key order of the set of
+ * ALL distinct k-mers (the set a cutoff <= 1 call returns); out holds n entries. */
+int kmsc_count_last_counts(kmsc_ctx* ctx, uint8_t* out, int64_t n);
 
 /* ---- P5: dense-bitmap Gram for K <= 15 ---------------------------------------------- */
 /* out[i*n + j] = |S_i & S_j| over 2^(2K)-bit bitmaps (exact all-bucket matrix);

@@ -284,4 +284,14 @@ int kmsc_count_get(kmsc_ctx* ctx, uint64_t kmer, int* count) {
   return KMSC_OK;
 }
 
+int kmsc_count_last_counts(kmsc_ctx* ctx, uint8_t* out, int64_t n) {
+  if (!ctx || (n > 0 && !out)) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  if (!ctx->last_counted || !ctx->last_counts) { set_error("no counter: call kmsc_count_fasta / kmsc_count_reads first"); return KMSC_E_STATE; }
+  if (n != ctx->last_counted->n_keys) { set_error("n=%lld but the counter holds %lld k-mers", (long long)n, (long long)ctx->last_counted->n_keys); return KMSC_E_INVALID; }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  if (n > 0) KMSC_CUDA(cudaMemcpyAsync(out, ctx->last_counts, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return KMSC_OK;
+}
+
 }  // extern "C"

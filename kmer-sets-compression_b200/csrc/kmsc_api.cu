@@ -180,12 +180,14 @@ int set_alloc(kmsc_ctx* ctx, int K, int N, int key_bytes, int64_t n_keys, kmsc_s
   s->K = K; s->N = N; s->key_bytes = key_bytes; s->key_bits = 2 * K - N;
   s->max_level = s->key_bits < kMaxFineLevel ? s->key_bits : kMaxFineLevel;
   s->n_keys = n_keys;
+  // stream-ordered allocations from the device's default pool (kept warm: no release
+  // threshold), so building / freeing sets every step costs microseconds, not cudaMalloc.
   // 64 bytes of slack so vectorised tail loads stay in bounds
-  cudaError_t e = cudaMalloc(&s->keys, (size_t)n_keys * key_bytes + 64);
-  if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc keys", __FILE__, __LINE__); }
+  cudaError_t e = cudaMallocAsync(&s->keys, (size_t)n_keys * key_bytes + 64, ctx->stream);
+  if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMallocAsync keys", __FILE__, __LINE__); }
   const uint64_t entries = levels_total_entries(N, s->max_level);
-  e = cudaMalloc(&s->lev_base, entries * sizeof(uint32_t));
-  if (e != cudaSuccess) { cudaFree(s->keys); delete s; return cuda_fail(e, "cudaMalloc levels", __FILE__, __LINE__); }
+  e = cudaMallocAsync((void**)&s->lev_base, entries * sizeof(uint32_t), ctx->stream);
+  if (e != cudaSuccess) { cudaFreeAsync(s->keys, ctx->stream); delete s; return cuda_fail(e, "cudaMallocAsync levels", __FILE__, __LINE__); }
   uint64_t start = 0;
   for (int f = 0; f <= s->max_level; f++) {
     s->lev[f] = s->lev_base + start;
@@ -283,6 +285,13 @@ int kmsc_ctx_create(int device, void* stream, kmsc_ctx** out) {
   if (prop.major < 10) {
     set_error("device %d is sm_%d%d; libkmsc is built for sm_100a only", device, prop.major, prop.minor);
     return KMSC_E_CUDA;
+  }
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
   }
   kmsc_ctx* c = new kmsc_ctx();
   c->device = device;
@@ -404,11 +413,14 @@ void kmsc_set_free(kmsc_ctx* ctx, kmsc_set* set) {
   if (!set) return;
   if (ctx) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
     if (ctx->last_counted == set) ctx->last_counted = nullptr;
+    // stream-ordered free: everything enqueued so far that reads the set completes first
+    if (set->keys) cudaFreeAsync(set->keys, ctx->stream);
+    if (set->lev_base) cudaFreeAsync(set->lev_base, ctx->stream);
+  } else {
+    if (set->keys) cudaFree(set->keys);
+    if (set->lev_base) cudaFree(set->lev_base);
   }
-  if (set->keys) cudaFree(set->keys);
-  if (set->lev_base) cudaFree(set->lev_base);
   delete set;
 }
 

@@ -4,7 +4,6 @@
 using namespace kmsc;
 #define KMSC_STUB(name) set_error(name ": not built yet in this revision"); return KMSC_E_STATE;
 extern "C" {
-int kmsc_bitmap_gram(kmsc_ctx*, const kmsc_set* const*, int32_t, int64_t*) { KMSC_STUB("kmsc_bitmap_gram") }
 int kmsc_codec_encode(kmsc_ctx*, const kmsc_set*, uint8_t**, int64_t*) { KMSC_STUB("kmsc_codec_encode") }
 int kmsc_codec_decode(kmsc_ctx*, const uint8_t*, int64_t, kmsc_set**) { KMSC_STUB("kmsc_codec_decode") }
 }

@@ -1,0 +1,140 @@
+// kmsc/kmer_set_compact.h -- KmerSetCompact<K,N,KeyType> with the reference's
+// interface (lib/core/kmer_set_compact.h:31-347): an immutable SPSS store, two bits
+// per base plus string lengths (minus K) in streamvbyte-0124. Same text file format
+// (one SPSS string per line, optional external (de)compressor). The decode paths
+// GetSampledKmerSet / ToKmerSet run on the GPU from the packed words
+// (kmsc_set_from_packed): no ASCII is re-materialised.
+#ifndef KMSC_HOST_KMER_SET_COMPACT_H_
+#define KMSC_HOST_KMER_SET_COMPACT_H_
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "kmsc/io.h"
+#include "kmsc/kmer_set.h"
+#include "kmsc/spss.h"
+#include "kmsc/streamvbyte0124.h"
+
+namespace kmsc {
+
+template <int K, int N, typename KeyType>
+class KmerSetCompact {
+ public:
+  KmerSetCompact() = default;
+
+  static KmerSetCompact FromKmerSet(const KmerSet<K, N, KeyType>& kmer_set, bool canonical, bool fast, int n_workers) {
+    std::vector<std::string> spss =
+        canonical ? GetSPSSCanonical<K, N, KeyType>(kmer_set, fast, n_workers) : GetSPSS<K, N, KeyType>(kmer_set, n_workers);
+    return KmerSetCompact(spss);
+  }
+  static KmerSetCompact FromStrings(const std::vector<std::string>& spss) { return KmerSetCompact(spss); }
+
+  KmerSet<K, N, KeyType> ToKmerSet(bool canonical, int /*n_workers*/) const {
+    return KmerSet<K, N, KeyType>(MakeSetPtr(Decode(canonical, /*dedup=*/true, 0, 1 << N)));
+  }
+
+  Status Dump(const std::string& file_name, const std::string& compressor, int n_workers) const {
+    return WriteLines(file_name, compressor, ToStrings(n_workers));
+  }
+  static StatusOr<KmerSetCompact> Load(const std::string& file_name, const std::string& decompressor) {
+    StatusOr<std::vector<std::string>> lines = ReadLines(file_name, decompressor);
+    if (!lines.ok()) return lines.status();
+    return KmerSetCompact(lines.value());
+  }
+
+  std::int64_t Size(int /*n_workers*/) const {
+    std::int64_t s = 0;
+    for (std::uint32_t l : Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_))) s += static_cast<std::int64_t>(l) + 1;
+    return s;
+  }
+  std::int64_t Weight() const { return n_bases_; }
+
+  // sorted keys of the selected buckets, indexed by position in bucket_ids; duplicates
+  // kept; a bucket id listed twice is filled only at its last position (reference :127-131)
+  std::vector<std::vector<KeyType>> GetSampledKmerSet(const std::vector<int>& bucket_ids, bool canonical,
+                                                      int /*n_workers*/) const {
+    std::vector<std::vector<KeyType>> buckets(bucket_ids.size());
+    if (bucket_ids.empty()) return buckets;
+    int lo = bucket_ids[0], hi = bucket_ids[0];
+    for (int b : bucket_ids) { lo = b < lo ? b : lo; hi = b > hi ? b : hi; }
+    kmsc_set* s = Decode(canonical, /*dedup=*/false, lo, hi + 1);
+    std::vector<std::int64_t> offs((std::size_t(1) << N) + 1);
+    std::int64_t n = 0;
+    std::vector<KeyType> keys;
+    {
+      std::lock_guard<std::mutex> l(Device::Mu());
+      Device::Check(kmsc_set_size(Device::Ctx(), s, &n), "kmsc_set_size");
+      keys.resize(static_cast<std::size_t>(n));
+      Device::Check(kmsc_set_to_csr(Device::Ctx(), s, offs.data(), keys.data()), "kmsc_set_to_csr");
+      kmsc_set_free(Device::Ctx(), s);
+    }
+    std::unordered_map<int, std::size_t> last;
+    for (std::size_t i = 0; i < bucket_ids.size(); i++) last[bucket_ids[i]] = i;
+    for (const auto& p : last) {
+      const std::size_t b = static_cast<std::size_t>(p.first);
+      buckets[p.second].assign(keys.begin() + offs[b], keys.begin() + offs[b + 1]);
+    }
+    return buckets;
+  }
+
+  // the device set of the k-mers in [bucket_lo, bucket_hi) (a rank's prefix shard)
+  KmerSet<K, N, KeyType> ToKmerSetShard(bool canonical, int bucket_lo, int bucket_hi) const {
+    return KmerSet<K, N, KeyType>(MakeSetPtr(Decode(canonical, true, bucket_lo, bucket_hi)));
+  }
+
+  std::vector<std::string> ToStrings(int /*n_workers*/) const {
+    const std::vector<std::uint32_t> lens = Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_));
+    std::vector<std::string> out(static_cast<std::size_t>(n_));
+    std::int64_t pos = 0;
+    for (std::int64_t i = 0; i < n_; i++) {
+      const std::int64_t len = static_cast<std::int64_t>(lens[static_cast<std::size_t>(i)]) + K;
+      std::string& s = out[static_cast<std::size_t>(i)];
+      s.resize(static_cast<std::size_t>(len));
+      for (std::int64_t j = 0; j < len; j++, pos++)
+        s[static_cast<std::size_t>(j)] = "ACGT"[(words_[static_cast<std::size_t>(pos >> 5)] >> (62 - 2 * (pos & 31))) & 3];
+    }
+    return out;
+  }
+
+ private:
+  explicit KmerSetCompact(const std::vector<std::string>& spss) {
+    n_ = static_cast<std::int64_t>(spss.size());
+    std::vector<std::uint32_t> lengths(spss.size());
+    std::int64_t total = 0;
+    for (std::size_t i = 0; i < spss.size(); i++) {
+      lengths[i] = static_cast<std::uint32_t>(spss[i].size()) - K;
+      total += static_cast<std::int64_t>(spss[i].size());
+    }
+    n_bases_ = total;
+    words_.assign(static_cast<std::size_t>((total + 31) / 32 + 2), 0);
+    std::int64_t pos = 0;
+    for (const std::string& s : spss)
+      for (char c : s) {
+        words_[static_cast<std::size_t>(pos >> 5)] |= Kmer<K>::Code(c) << (62 - 2 * (pos & 31));
+        pos++;
+      }
+    lengths_compressed_ = Svb0124Encode(lengths);
+  }
+
+  kmsc_set* Decode(bool canonical, bool dedup, int bucket_lo, int bucket_hi) const {
+    const std::vector<std::uint32_t> lens = Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_));
+    std::vector<std::int64_t> offs(static_cast<std::size_t>(n_) + 1, 0);
+    for (std::int64_t i = 0; i < n_; i++)
+      offs[static_cast<std::size_t>(i) + 1] = offs[static_cast<std::size_t>(i)] + lens[static_cast<std::size_t>(i)] + K;
+    kmsc_set* s = nullptr;
+    std::lock_guard<std::mutex> l(Device::Mu());
+    Device::Check(kmsc_set_from_packed(Device::Ctx(), K, N, static_cast<int>(sizeof(KeyType)), words_.data(), offs.data(), n_,
+                                       canonical ? 1 : 0, dedup ? 1 : 0, bucket_lo, bucket_hi, &s), "kmsc_set_from_packed");
+    return s;
+  }
+
+  std::int64_t n_ = 0;                            // number of strings
+  std::int64_t n_bases_ = 0;                      // sum of string lengths = Weight()
+  std::vector<std::uint8_t> lengths_compressed_;  // length - K per string, streamvbyte 0124
+  std::vector<std::uint64_t> words_;              // 2 bits per base, 32 bases per word, first base on top
+};
+
+}  // namespace kmsc
+#endif

@@ -1,0 +1,60 @@
+// kmerset-multiple-compress -- drop-in for the reference executable
+// (src/kmerset-multiple-compress.cc:33-163): same flags (--k --workers --canonical
+// --decompressor --compressor --out --extension --out_graph), same input (one SPSS text
+// file per set) and the same output directory format (meta.<ext> + <i>.<ext>, DOT graph).
+// Extra flags: --exact (all-bucket weights instead of the 2% sample), --seed (bucket sample).
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "flags.h"
+#include "kmsc/kmer_set_compact.h"
+#include "kmsc/kmer_set_set.h"
+
+using namespace kmsc;
+using namespace kmsc_cli;
+
+template <int K, int N, typename KeyType>
+int Main(const Flags& flags) {
+  const int n_workers = flags.Int("workers", 1);
+  const bool canonical = flags.Bool("canonical", true);
+  const std::string decompressor = flags.Str("decompressor", "");
+  const std::vector<std::string>& files = flags.positional;
+  std::vector<KmerSetCompact<K, N, KeyType>> sets(files.size());
+  for (std::size_t i = 0; i < files.size(); i++) {
+    Info("loading file: " + files[i]);
+    auto r = KmerSetCompact<K, N, KeyType>::Load(files[i], decompressor);
+    if (!r.ok()) { Error("failed to load file: " + r.status().ToString()); return 1; }
+    sets[i] = std::move(r).value();
+  }
+  for (std::size_t i = 0; i < sets.size(); i++)
+    Info("i = " + std::to_string(i) + ", size = " + std::to_string(sets[i].Size(n_workers)));
+  Info("constructing kmer_set_set");
+  KmerSetSetOptions opt;
+  opt.exact = flags.Bool("exact", false);
+  opt.seed = static_cast<std::uint64_t>(flags.Int("seed", 0));
+  KmerSetSet<K, N, KeyType> kss(std::move(sets), canonical, n_workers, opt);
+  Info("constructed kmer_set_set, size = " + std::to_string(kss.Size()));
+  const std::string out_graph = flags.Str("out_graph", "");
+  if (!out_graph.empty()) {
+    Status st = kss.DumpGraph(out_graph);
+    if (!st.ok()) { Error("failed to dump graph: " + st.ToString()); return 1; }
+  }
+  const std::string out = flags.Str("out", "");
+  if (!out.empty()) {
+    Status st = kss.Dump(out, flags.Str("compressor", ""), flags.Str("extension", "txt"), n_workers);
+    if (!st.ok()) { Error("failed to dump kmer_set_set: " + st.ToString()); return 1; }
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  const Flags flags = ParseFlags(argc, argv, {"debug", "canonical", "exact"});
+  switch (flags.Int("k", 15)) {  // the reference's instantiations (:149-157)
+    case 15: return Main<15, 14, std::uint16_t>(flags);
+    case 19: return Main<19, 10, std::uint32_t>(flags);
+    case 23: return Main<23, 14, std::uint32_t>(flags);
+    case 31: return Main<31, 14, std::uint64_t>(flags);
+    default: Error("unsupported k"); return 1;
+  }
+}

@@ -32,7 +32,7 @@ EXPORTS = [
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
     "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
-    "kmsc_count_get", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
+    "kmsc_count_get", "kmsc_count_last_counts", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
 ]
 
 
@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
                                    C.POINTER(C.c_void_p), _i64p, _i64p]
     L.kmsc_count_reads.argtypes = L.kmsc_count_fasta.argtypes
     L.kmsc_count_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    L.kmsc_count_last_counts.argtypes = [C.c_void_p, _u8p, C.c_int64]
     L.kmsc_bitmap_gram.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i64p]
     L.kmsc_codec_encode.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
     L.kmsc_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
@@ -299,6 +300,11 @@ class Context:
         v = C.c_int()
         _check(lib().kmsc_count_get(self.h, kmer, C.byref(v)))
         return v.value
+
+    def count_last_counts(self, n: int) -> np.ndarray:
+        out = np.zeros(max(1, n), np.uint8)
+        _check(lib().kmsc_count_last_counts(self.h, out.ctypes.data_as(_u8p), n))
+        return out[:n]
 
     # -- P5 / P6 ------------------------------------------------------------------------
     def bitmap_gram(self, sets):

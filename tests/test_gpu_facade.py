@@ -1,0 +1,75 @@
+"""Host side (C++17 facade + drop-in executables) on a GPU:
+ * tests/cpp/facade_test.cc restates the reference's own gtest cases (test/kmer.cc,
+   kmer_set.cc, kmer_counter.cc, kmer_set_compact.cc, kmer_set_set.cc,
+   parallel_disjoint_set.cc, spss.cc) against the kmsc classes of the same names;
+ * the three executables run end to end: kmerset-build -> kmerset-multiple-compress ->
+   kmerset-multiple-decompress, and the printed (size, XOR hash) of every reconstructed
+   set must equal the oracle's for the original input (the reference's end-to-end
+   observable, src/kmerset-multiple-decompress.cc:57-79)."""
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HOST = ROOT / "kmer-sets-compression_b200" / "host"
+sys.path.insert(0, str(ROOT / "kmer-sets-compression_b200"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bins():
+    r = subprocess.run(["make", "-s", "-C", str(HOST)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return HOST / "bin"
+
+
+def test_facade_cases(bins):
+    r = subprocess.run([str(bins / "facade_test")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("K", [15, 23])
+def test_cli_end_to_end(bins, oracle, tmp_path, K):
+    import synth
+    rng = np.random.default_rng(K)
+    seqs = synth.phylogeny_sequences(5, 6000, p=0.02, seed=K)
+    spss_files, want = [], []
+    for i, s in enumerate(seqs):
+        # reads covering the sequence 3x -> FASTA -> kmerset-build (cutoff 2 drops nothing that is covered twice)
+        txt = synth.to_ascii(s).decode()
+        fasta = tmp_path / f"in{i}.fa"
+        lines = []
+        for rep in range(3):
+            for a in range(0, len(txt) - 200, 150):
+                lines += [f">r{rep}_{a}", txt[a:a + 230]]
+        fasta.write_text("\n".join(lines) + "\n")
+        reads = lines[1::2]
+        kmers, counts = oracle.count_reads(reads, K, True)
+        kept, _ = oracle.counter_to_set(kmers, counts, 2)
+        want.append((len(kept), oracle.set_hash(kept)))
+        out = tmp_path / f"set{i}.txt"
+        r = subprocess.run([str(bins / "kmerset-build"), f"--k={K}", "--cutoff=2", "--check", f"--out={out}", str(fasta)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert f"kmer_set.Size() = {len(kept)}" in r.stderr and f"kmer_set.Hash() = {oracle.set_hash(kept)}" in r.stderr
+        assert "kmer_set_compact -> KmerSet: ok" in r.stderr
+        spss_files.append(str(out))
+    outdir = tmp_path / "dump"
+    r = subprocess.run([str(bins / "kmerset-multiple-compress"), f"--k={K}", f"--out={outdir}", "--seed=3",
+                        f"--out_graph={tmp_path / 'g.dot'}"] + spss_files, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    meta = (outdir / "meta.txt").read_text().split("\n")
+    n_nodes = int(meta[1])
+    assert n_nodes >= 5 and (outdir / f"{n_nodes - 1}.txt").exists()
+    assert (tmp_path / "g.dot").read_text().startswith("digraph G {")
+    r = subprocess.run([str(bins / "kmerset-multiple-decompress"), f"--k={K}", "--n=5", str(outdir)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    hashes = [int(x) for x in re.findall(r"kmer_set.Hash\(\) = (\d+)", r.stderr)]
+    sizes = [int(x) for x in re.findall(r"kmer_set.Size\(\) = (\d+)", r.stderr)]
+    assert list(zip(sizes, hashes)) == want
