@@ -21,10 +21,12 @@
 //   B_w = sum_i sum_{b in B} len_i[b] * sizeof(KeyType)  (+ offsets + n*n*8).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "kmsc_common.cuh"
+#include "umma.cuh"
 
 namespace kmsc {
 
@@ -202,29 +204,35 @@ __global__ void plan_emit_kernel(const uint32_t* __restrict__ totals, PlanParams
 }
 
 // ---------------------------------------------------------------------------
-// main kernel
+// main kernel: shared-memory hash build + tensor-core Gram (tcgen05 kind::i8)
 // ---------------------------------------------------------------------------
+//
+// One persistent CTA per (SM x occupancy) pulls tiles from an atomic counter. Per tile:
+//   build    every key of every set in the tile is looked up / inserted in an open-addressing
+//            table in shared memory: slot = key + NS-bit membership mask. Warp w owns the
+//            sets [w * spw, (w + 1) * spw) and the mask byte w of every slot, so marking
+//            membership is a plain byte read-modify-write (no shared atomics).
+//   compact  the occupied slots are listed (ballot scan of the table).
+//   gram     32 distinct keys at a time, the masks are expanded to 0/1 bytes in the MN-major
+//            operand layout of umma.cuh (lane = key: no transpose) and W += X X^T is issued as
+//            tcgen05.mma kind::i8 with int32 accumulators that stay in tensor memory for the
+//            CTA's lifetime. The expansion of chunk c + 1 overlaps the MMAs of chunk c (two
+//            staging buffers guarded by mbarriers); the MMAs of a tile's last chunks overlap
+//            the next tile's build.
+// At the end the accumulators are read back (tcgen05.ld) and added to W with 64-bit RED.
 
 template <typename KeyT> struct TableKey { using type = uint32_t; };
 template <> struct TableKey<unsigned long long> { using type = unsigned long long; };
 
-// per mask-width configuration: table slots, max distinct keys per pass, threads,
-// gram chunk in 32-key words. Sized so MW<=4 fits two CTAs per SM (228 KB).
-template <int MW> struct PcCfg;
-// UNR = keys in flight per lane, MINB = CTAs per SM the register budget is sized for.
-#ifndef PC_MW2_SMALL
-#define PC_MW2_SMALL 1
-#endif
-template <> struct PcCfg<1> { static constexpr int S = 8192, LOG2S = 13, D = 4096, T = 256, CW = 32, UNR = 8, MINB = 2; };
-#if PC_MW2_SMALL
-template <> struct PcCfg<2> { static constexpr int S = 4096, LOG2S = 12, D = 1536, T = 256, CW = 8, UNR = 4, MINB = 4; };
-#else
-template <> struct PcCfg<2> { static constexpr int S = 8192, LOG2S = 13, D = 3072, T = 256, CW = 16, UNR = 8, MINB = 2; };
-#endif
-template <> struct PcCfg<4> { static constexpr int S = 4096, LOG2S = 12, D = 2048, T = 256, CW = 16, UNR = 8, MINB = 1; };
-template <> struct PcCfg<8> { static constexpr int S = 4096, LOG2S = 12, D = 2048, T = 512, CW = 16, UNR = 4, MINB = 1; };
+// NS = padded set count = rows of the Gram (64 / 128 / 256); TKB = bytes of a table key.
+//   S slots, D = max distinct keys per pass, T threads (one warp per 8 sets),
+//   CK = K-steps (32 keys) per staging buffer, UNR = key rows in flight per warp.
+template <int NS, int TKB> struct PcCfg;
+template <int TKB> struct PcCfg<64, TKB>  { static constexpr int S = 4096, LOG2S = 12, D = 2560, T = 256,  CK = 4, UNR = 4, MINB = 3; };
+template <int TKB> struct PcCfg<128, TKB> { static constexpr int S = 2048, LOG2S = 11, D = 1280, T = 512,  CK = 4, UNR = 4, MINB = 2; };
+template <> struct PcCfg<256, 4>          { static constexpr int S = 4096, LOG2S = 12, D = 2560, T = 1024, CK = 4, UNR = 2, MINB = 1; };
+template <> struct PcCfg<256, 8>          { static constexpr int S = 2048, LOG2S = 11, D = 1280, T = 1024, CK = 4, UNR = 2, MINB = 1; };
 
-constexpr int kSeg = 256;         // keys per build work item
 constexpr int kStackMax = 48;
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t k, int log2s) {
@@ -242,349 +250,266 @@ __device__ __forceinline__ uint32_t hash_class(unsigned long long k) {
   return (uint32_t)(h >> 32) ^ (uint32_t)h;
 }
 
-// 32x32 bit-matrix transpose across a warp: in = row `lane`, out = column `lane`.
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
-#pragma unroll
-  for (int k = 16; k >= 1; k >>= 1) {
-    // mask of columns c with (c & k) == 0
-    const uint32_t mlow = (k == 16) ? 0x0000FFFFu : (k == 8) ? 0x00FF00FFu : (k == 4) ? 0x0F0F0F0Fu
-                        : (k == 2) ? 0x33333333u : 0x55555555u;
-    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
-    if (lane & k) x = (x & ~mlow) | ((y >> k) & mlow);
-    else          x = (x & mlow) | ((y << k) & ~mlow);
-  }
-  return x;
-}
-
 // Shared-memory layout with compile-time offsets (so every access keeps the
 // shared address space: LDS / STS / ATOMS, not generic LD / ST).
-template <typename TK, int MW>
+template <typename TK, int NS>
 struct PcLayout {
-  using C = PcCfg<MW>;
-  static constexpr size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
-  static constexpr int NPAD = 32 * MW;
-  static constexpr int NB4 = NPAD / 4;
-  static constexpr size_t o_keys = 0;
-  static constexpr size_t o_mask = a16((size_t)(C::S + 1) * sizeof(TK));
-  static constexpr size_t o_colT = a16(o_mask + (size_t)(C::S + 1) * MW * 4);
-  static constexpr size_t o_order = o_colT + (size_t)C::CW * NPAD * 4;
-  static constexpr size_t o_kp = a16(o_order + (size_t)(C::D + 1) * 2);
-  static constexpr size_t o_sbeg = o_kp + (size_t)NPAD * 8;
-  static constexpr size_t o_send = o_sbeg + (size_t)NPAD * 4;
-  static constexpr size_t o_segpre = o_send + (size_t)NPAD * 4;
-  static constexpr size_t o_misc = o_segpre + (size_t)NPAD * 4;
-  static constexpr size_t o_stack = o_misc + 64 * 4;
-  static constexpr size_t o_blk = o_stack + (size_t)kStackMax * 8;
-  static constexpr size_t total = a16(o_blk + (size_t)(NB4 * (NB4 + 1) / 2) * 2);
+  using C = PcCfg<NS, (int)sizeof(TK)>;
+  static constexpr int MW = NS / 32;
+  static constexpr size_t al(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }
+  static constexpr size_t kstep_bytes = (size_t)NS * 32;             // one K-step of the operand
+  static constexpr size_t buf_bytes = kstep_bytes * C::CK;           // one staging buffer
+  static constexpr size_t o_stage = 0;                               // 2 buffers, 128-byte aligned
+  static constexpr size_t o_keys = al(o_stage + 2 * buf_bytes, 16);
+  static constexpr size_t o_mask = al(o_keys + (size_t)(C::S + 1) * sizeof(TK), 16);
+  static constexpr size_t o_list = al(o_mask + (size_t)(C::S + 1) * MW * 4, 16);
+  static constexpr size_t o_kp = al(o_list + (size_t)(C::D + 2) * 2, 16);
+  static constexpr size_t o_sbeg = o_kp + (size_t)NS * 8;
+  static constexpr size_t o_send = o_sbeg + (size_t)NS * 4 * 2;   // two tiles: current, next
+  static constexpr size_t o_misc = o_send + (size_t)NS * 4 * 2;
+  static constexpr size_t o_stack = o_misc + 16 * 4;
+  static constexpr size_t o_bar = al(o_stack + (size_t)kStackMax * 8, 8);
+  static constexpr size_t total = al(o_bar + 2 * 8, 16);
 };
 
 // misc[] slots
-constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscItems = 3, kMiscSp = 4, kMiscSpecial = 5,
-              kMiscWsum = 8;
+constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscSp = 3, kMiscSpecial = 4, kMiscTmem = 5,
+              kMiscAnyMma = 6, kMiscNext = 7;
 
-#ifndef PC_SLOW
-#define PC_SLOW 0      // 0 = divergent per-lane slow path, 1 = warp-convergent resolve_row
-#endif
-#ifndef PC_BUCKET2
-#define PC_BUCKET2 0   // 1 = two-slot buckets: the first probe reads slots h, h+1 with one 64-bit load
-#endif
-
-// Slow path, per lane (divergent): the first probe at slot h returned `c` != key.
-// An EMPTY first probe goes straight to the CAS; other keys probe linearly.
-template <typename TK, int S, int DMAX>
-__device__ __forceinline__ uint32_t find_slot_slow(TK* skeys, uint16_t* order, int* misc, TK key, uint32_t h, TK c) {
+// The table is probed two slots at a time: slots (h, h + 1) with h even are one 8 / 16-byte
+// load. Slow path, per lane (divergent, rare): neither slot of the home pair held the key
+// or could be claimed. Walks the following pairs; an empty slot is claimed with CAS. A probe
+// sequence longer than the table means the table is full: flag overflow (the pass is
+// repeated on a split class).
+template <typename TK, int S>
+__device__ __forceinline__ uint32_t find_slot_slow(TK* skeys, int* misc, TK key, uint32_t h) {
   const TK EMPTY = (TK)~(TK)0;
-  if (sizeof(TK) == 4 && key == EMPTY) {
-    // the one key that collides with the empty marker lives in the extra slot S
-    if (atomicExch(&misc[kMiscSpecial], 1) == 0) {
-      const int r = atomicAdd(&misc[kMiscNdist], 1);
-      if (r < DMAX) order[r] = (uint16_t)S; else misc[kMiscOverflow] = 1;
-    }
-    return S;
-  }
-  for (;;) {
+  for (int n = 0; n <= S; n++) {
+    const TK c = skeys[h];
+    if (c == key) return h;
     if (c == EMPTY) {
       const TK old = atomicCAS(&skeys[h], EMPTY, key);
-      if (old == EMPTY) {
-        const int r = atomicAdd(&misc[kMiscNdist], 1);
-        if (r < DMAX) order[r] = (uint16_t)h; else misc[kMiscOverflow] = 1;
-        return h;
-      }
-      if (old == key) return h;
+      if (old == EMPTY || old == key) return h;
     }
     h = (h + 1) & (S - 1);
-    c = skeys[h];
-    if (c == key) return h;
   }
+  misc[kMiscOverflow] = 1;
+  return S;  // harmless: the pass is discarded
 }
 
-// Slow path of the table lookup, warp-convergent: called by ALL 32 lanes of a warp
-// for one row of keys; lanes with `pend` set missed their first probe (empty slot,
-// another key, or the key equals the empty marker). Every iteration advances all
-// pending lanes by one probe; new keys get their rank in `order` through one
-// warp-aggregated shared atomic. Returns the slot of `key`.
-template <typename TK, int S, int DMAX>
-__device__ __forceinline__ uint32_t resolve_row(TK* skeys, uint16_t* order, int* misc, TK key, uint32_t h,
-                                               bool pend, int lane) {
-  const TK EMPTY = (TK)~(TK)0;
-  bool inserted = false;
-  if (sizeof(TK) == 4) {
-    // the one key that collides with the empty marker lives in the extra slot S
-    const bool sp = pend && key == EMPTY;
-    if (__any_sync(0xffffffffu, sp)) {
-      if (sp) {
-        h = S;
-        pend = false;
-        if (atomicExch(&misc[kMiscSpecial], 1) == 0) inserted = true;
-      }
-    }
+template <typename TK> struct SlotPair;
+template <> struct SlotPair<uint32_t> {
+  static __device__ __forceinline__ void load(const uint32_t* p, uint32_t& a, uint32_t& b) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    a = v.x; b = v.y;
   }
-  while (__any_sync(0xffffffffu, pend)) {
-    if (pend) {
-      const TK c = skeys[h];
-      if (c == key) {
-        pend = false;
-      } else if (c == EMPTY) {
-        const TK old = atomicCAS(&skeys[h], EMPTY, key);
-        if (old == EMPTY) { inserted = true; pend = false; }
-        else if (old == key) pend = false;
-        else h = (h + 1) & (S - 1);
-      } else {
-        h = (h + 1) & (S - 1);
-      }
-    }
+};
+template <> struct SlotPair<unsigned long long> {
+  static __device__ __forceinline__ void load(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    a = v.x; b = v.y;
   }
-  const unsigned im = __ballot_sync(0xffffffffu, inserted);
-  if (im) {
-    const int leader = __ffs(im) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&misc[kMiscNdist], __popc(im));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (inserted) {
-      const int r = base + __popc(im & ((1u << lane) - 1u));
-      if (r < DMAX) order[r] = (uint16_t)h; else misc[kMiscOverflow] = 1;
-    }
-  }
-  return h;
-}
+};
 
-// Insert keys [beg, end) of set s (table key = top | key) and mark membership.
-// U keys per lane are handled as a batch: U independent global loads, U independent
-// first probes, then the (rare) slow paths, then U membership marks.
-// OWN: the mask byte (slot, s / 8) is only ever touched by the warp that owns set
-// group s / 8, and the keys of one set are distinct, so a plain byte
-// read-modify-write is race free (ordered across sets by __syncwarp). Otherwise a
-// shared-memory atomicOr on the mask word.
-template <typename KeyT, typename TK, int MW, bool OWN, int U, bool FULL>
-__device__ __forceinline__ void process_batch(TK* skeys, uint32_t* smask, uint16_t* order, int* misc,
-                                              const KeyT* __restrict__ kp, uint32_t i0, uint32_t end, TK top,
-                                              int s, int lane, uint32_t cmask, uint32_t cp) {
-  using C = PcCfg<MW>;
+// Insert keys [i0, i0 + 32 U) of one set (table key = top | key) and set bit `bit` of the mask
+// byte `byte_idx` this warp owns. U rows of 32 keys are handled as a batch: U independent
+// coalesced global loads, U independent pair probes, claims of empty slots, the rare slow
+// paths, U marks. The keys of one set are distinct, so the U marks of a batch never hit the
+// same byte. CLS: only keys of hash class (cmask, cp) take part (after a table overflow).
+template <typename KeyT, typename TK, int NS, int U, bool FULL, bool CLS>
+__device__ __forceinline__ void process_batch(TK* skeys, uint8_t* maskb, int* misc, const KeyT* __restrict__ kp,
+                                              uint32_t i0, uint32_t end, TK top, int byte_idx, uint32_t bit,
+                                              int lane, uint32_t cmask, uint32_t cp) {
+  using C = PcCfg<NS, (int)sizeof(TK)>;
+  constexpr int MWB = NS / 8;  // mask bytes per slot
   const TK EMPTY = (TK)~(TK)0;
-  uint8_t* maskb = reinterpret_cast<uint8_t*>(smask);
   KeyT kk[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
     const uint32_t i = i0 + u * 32 + lane;
     kk[u] = (FULL || i < end) ? __ldg(kp + i) : (KeyT)0;
   }
-  TK key[U];
+  TK key[U], c0[U], c1[U];
   uint32_t h[U];
   bool act[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
     const uint32_t i = i0 + u * 32 + lane;
     key[u] = top | (TK)kk[u];
-    act[u] = (FULL || i < end) && (!cmask || (hash_class(key[u]) & cmask) == cp);
-    h[u] = hash_slot(key[u], C::LOG2S);
+    act[u] = FULL || i < end;
+    if (CLS) act[u] = act[u] && (hash_class(key[u]) & cmask) == cp;
+    h[u] = hash_slot(key[u], C::LOG2S) & ~1u;
   }
-#if PC_BUCKET2
-  // two-slot buckets: slots (h & ~1, h | 1) are read with one 64-bit load
-  TK c0[U], c1[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) SlotPair<TK>::load(&skeys[h[u]], c0[u], c1[u]);
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    h[u] &= ~1u;
-    if (sizeof(TK) == 4) {
-      const uint2 v = *reinterpret_cast<const uint2*>(&skeys[h[u]]);
-      c0[u] = (TK)v.x; c1[u] = (TK)v.y;
-    } else {
-      c0[u] = skeys[h[u]]; c1[u] = skeys[h[u] + 1];
+    bool pend = act[u] && c0[u] != key[u];
+    if (c1[u] == key[u]) { h[u] += 1; pend = false; }
+    if (sizeof(TK) == 4 && key[u] == EMPTY) {
+      // the one key that collides with the empty marker lives in the extra slot S
+      if (act[u]) misc[kMiscSpecial] = 1;
+      h[u] = C::S;
+      pend = false;
     }
-  }
-#pragma unroll
-  for (int u = 0; u < U; u++) {
-    const bool sp = sizeof(TK) == 4 && key[u] == EMPTY;
-    if (!sp && c1[u] == key[u]) { h[u] += 1; }
-    else if (sp || c0[u] != key[u]) {
-      if (act[u]) {
-        // first empty of the pair, else continue after the bucket
-        TK c = c0[u];
-        uint32_t hh = h[u];
-        if (c0[u] != EMPTY) { hh += 1; c = c1[u]; }
-        h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], hh, c);
+    if (pend) {
+      // new key (or a collision): claim the first empty slot of the pair
+      uint32_t hh = h[u];
+      bool done = false;
+      if (c0[u] == EMPTY) {
+        const TK old = atomicCAS(&skeys[hh], EMPTY, key[u]);
+        done = (old == EMPTY) || (old == key[u]);
       }
+      if (!done && c1[u] == EMPTY) {
+        hh += 1;
+        const TK old = atomicCAS(&skeys[hh], EMPTY, key[u]);
+        done = (old == EMPTY) || (old == key[u]);
+      }
+      if (!done) hh = find_slot_slow<TK, C::S>(skeys, misc, key[u], h[u]);
+      h[u] = hh;
     }
   }
-#else
-  TK cur[U];
+  uint8_t mv[U];
 #pragma unroll
-  for (int u = 0; u < U; u++) cur[u] = skeys[h[u]];
+  for (int u = 0; u < U; u++) mv[u] = maskb[h[u] * MWB + byte_idx];
 #pragma unroll
-  for (int u = 0; u < U; u++) {
-    const bool pend = act[u] && (cur[u] != key[u] || (sizeof(TK) == 4 && key[u] == EMPTY));
-#if PC_SLOW == 1
-    if (__any_sync(0xffffffffu, pend))  // warp-uniform
-      h[u] = resolve_row<TK, C::S, C::D>(skeys, order, misc, key[u], h[u], pend, lane);
-#else
-    if (pend) h[u] = find_slot_slow<TK, C::S, C::D>(skeys, order, misc, key[u], h[u], cur[u]);
-#endif
-  }
-#endif
-  if (OWN) {
-    uint8_t mv[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) mv[u] = maskb[h[u] * (MW * 4) + (s >> 3)];
-#pragma unroll
-    for (int u = 0; u < U; u++)
-      if (act[u]) maskb[h[u] * (MW * 4) + (s >> 3)] = (uint8_t)(mv[u] | (1u << (s & 7)));
-  } else {
-#pragma unroll
-    for (int u = 0; u < U; u++)
-      if (act[u]) atomicOr(&smask[h[u] * MW + ((uint32_t)s >> 5)], 1u << (s & 31));
-  }
+  for (int u = 0; u < U; u++)
+    if (act[u]) maskb[h[u] * MWB + byte_idx] = (uint8_t)(mv[u] | bit);
 }
 
-template <typename KeyT, typename TK, int MW, bool OWN, int UNR>
-__device__ __forceinline__ void process_run(TK* skeys, uint32_t* smask, uint16_t* order, int* misc,
-                                            const KeyT* __restrict__ kp, uint32_t beg, uint32_t end, TK top,
-                                            int s, int lane, uint32_t cmask, uint32_t cp) {
+template <typename KeyT, typename TK, int NS, int UNR, bool CLS>
+__device__ __forceinline__ void process_run(TK* skeys, uint8_t* maskb, int* misc, const KeyT* __restrict__ kp,
+                                            uint32_t beg, uint32_t end, TK top, int byte_idx, uint32_t bit,
+                                            int lane, uint32_t cmask, uint32_t cp) {
   uint32_t i0 = beg;
   // full batches: no bounds checks
   for (; i0 + 32 * UNR <= end; i0 += 32 * UNR) {
-    process_batch<KeyT, TK, MW, OWN, UNR, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
+    process_batch<KeyT, TK, NS, UNR, true, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
     if (*(volatile int*)&misc[kMiscOverflow]) return;
   }
-  // tail: rows of 32 keys in decreasing power-of-two batches
-  if (UNR >= 8 && i0 + 32 * 4 <= end) {
-    process_batch<KeyT, TK, MW, OWN, 4, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
-    i0 += 32 * 4;
-  }
-  if (UNR >= 4 && i0 + 32 * 2 <= end) {
-    process_batch<KeyT, TK, MW, OWN, 2, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
-    i0 += 32 * 2;
-  }
-  if (i0 + 32 <= end) {
-    process_batch<KeyT, TK, MW, OWN, 1, true>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
-    i0 += 32;
-  }
-  if (i0 < end) process_batch<KeyT, TK, MW, OWN, 1, false>(skeys, smask, order, misc, kp, i0, end, top, s, lane, cmask, cp);
+  if (i0 >= end) return;
+  // tail: 1 .. UNR - 1 full rows and possibly a partial one, as one bounds-checked batch
+  const uint32_t rows = (end - i0 + 31) >> 5;
+  if (UNR >= 4 && rows > 2)
+    process_batch<KeyT, TK, NS, UNR, false, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
+  else if (UNR >= 2 && rows == 2)
+    process_batch<KeyT, TK, NS, 2, false, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
+  else
+    process_batch<KeyT, TK, NS, 1, false, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
 }
 
-template <int MW>
+template <int NS>
 struct PcSmem {
   static size_t bytes(int tk_size) {
-    return tk_size == 8 ? PcLayout<unsigned long long, MW>::total : PcLayout<uint32_t, MW>::total;
+    return tk_size == 8 ? PcLayout<unsigned long long, NS>::total : PcLayout<uint32_t, NS>::total;
   }
 };
 
-template <typename KeyT, int MW>
-__global__ void __launch_bounds__(PcCfg<MW>::T, PcCfg<MW>::MINB)
-pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t* __restrict__ offsT,
+// Row / column p of the Gram <-> set index. Warp w owns sets [w * spw, (w + 1) * spw) and the
+// mask byte w, so set s sits at bit position 8 * (s / spw) + s % spw (spw <= 8; = s when spw = 8).
+__device__ __forceinline__ int set_of_pos(int p, int spw, int n_sets) {
+  const int r = p & 7;
+  const int s = (p >> 3) * spw + r;
+  return (r < spw && s < n_sets) ? s : -1;
+}
+
+template <typename KeyT, int NS>
+__global__ void __launch_bounds__(PcCfg<NS, (int)sizeof(typename TableKey<KeyT>::type)>::T,
+                                  PcCfg<NS, (int)sizeof(typename TableKey<KeyT>::type)>::MINB)
+pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const uint32_t* __restrict__ offsT,
                    const Tile* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_p,
                    uint32_t* __restrict__ tile_counter, unsigned long long* __restrict__ W,
                    unsigned long long* __restrict__ stats, int key_bits, int fine_level) {
-  using C = PcCfg<MW>;
   using TK = typename TableKey<KeyT>::type;
-  using LY = PcLayout<TK, MW>;
-  constexpr int S = C::S, DMAX = C::D, T = C::T, kChunkWords = C::CW;
-  constexpr int NPAD = 32 * MW;
-  constexpr int NW = T / 32;
-  constexpr bool OWN = MW >= 2;   // byte-ownership membership marks (no shared atomics)
-  constexpr int UNR = C::UNR;     // independent keys in flight per lane
+  using C = PcCfg<NS, (int)sizeof(TK)>;
+  using LY = PcLayout<TK, NS>;
+  constexpr int S = C::S, DMAX = C::D, T = C::T, CK = C::CK, UNR = C::UNR;
+  constexpr int MW = NS / 32;     // mask words per slot
+  constexpr int NW = T / 32;      // warps = mask bytes per slot
+  static_assert(NW == NS / 8, "one warp per mask byte");
+  constexpr int MMA_M = NS == 64 ? 64 : 128;
+  constexpr int MMA_N = NS;       // 64 / 128 / 256
+  constexpr int TMEM_COLS = NS == 256 ? 512 : NS;
   const TK EMPTY = (TK)~(TK)0;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* stage = smem_raw + LY::o_stage;
   TK* skeys = reinterpret_cast<TK*>(smem_raw + LY::o_keys);
   uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw + LY::o_mask);
-  uint32_t* colT = reinterpret_cast<uint32_t*>(smem_raw + LY::o_colT);
-  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + LY::o_order);
+  uint8_t* maskb = reinterpret_cast<uint8_t*>(smask);
+  uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + LY::o_list);
   const void** skp = reinterpret_cast<const void**>(smem_raw + LY::o_kp);
   uint32_t* sbeg = reinterpret_cast<uint32_t*>(smem_raw + LY::o_sbeg);
   uint32_t* send = reinterpret_cast<uint32_t*>(smem_raw + LY::o_send);
-  uint32_t* segpre = reinterpret_cast<uint32_t*>(smem_raw + LY::o_segpre);
   int* misc = reinterpret_cast<int*>(smem_raw + LY::o_misc);
   uint2* stack = reinterpret_cast<uint2*>(smem_raw + LY::o_stack);
-  uint8_t* blk_tab = reinterpret_cast<uint8_t*>(smem_raw + LY::o_blk);  // pairs (bi, bj)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LY::o_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NB4 = (n_sets + 3) / 4;
-  const int n_blocks = NB4 * (NB4 + 1) / 2;
-  constexpr int NB4MAX = NPAD / 4;
-  constexpr int NBLK = (NB4MAX * (NB4MAX + 1) / 2 + T - 1) / T;
 
   // one-time init
   for (int i = tid; i <= S; i += T) skeys[i] = EMPTY;
   for (int i = tid; i < (S + 1) * MW; i += T) smask[i] = 0;
-  for (int i = tid; i < NPAD; i += T) skp[i] = i < n_sets ? sets[i].keys : nullptr;
+  for (int i = tid; i < NS; i += T) skp[i] = i < n_sets ? sets[i].keys : nullptr;
   if (tid == 0) {
-    int q = 0;
-    for (int bi = 0; bi < NB4; bi++)
-      for (int bj = bi; bj < NB4; bj++) { blk_tab[2 * q] = (uint8_t)bi; blk_tab[2 * q + 1] = (uint8_t)bj; q++; }
-    misc[kMiscNdist] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0;
+    misc[kMiscNdist] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0; misc[kMiscAnyMma] = 0;
+    umma::mbar_init(&bar[0], 1);
+    umma::mbar_init(&bar[1], 1);
+    umma::mbar_fence_init();
   }
+  if (warp == 0) umma::tmem_alloc(reinterpret_cast<uint32_t*>(&misc[kMiscTmem]), TMEM_COLS);
+  umma::fence_before_thread_sync();
   __syncthreads();
-
-  int my_bi[NBLK], my_bj[NBLK];
-  uint32_t acc[NBLK][16];
-#pragma unroll
-  for (int t = 0; t < NBLK; t++) {
-    const int q = tid + t * T;
-    my_bi[t] = (q < n_blocks) ? blk_tab[2 * q] : -1;
-    my_bj[t] = (q < n_blocks) ? blk_tab[2 * q + 1] : -1;
-#pragma unroll
-    for (int e = 0; e < 16; e++) acc[t][e] = 0;
-  }
+  umma::fence_after_thread_sync();
+  const uint32_t tmem_base = (uint32_t)misc[kMiscTmem];
+  const uint32_t stage_addr = umma::smem_u32(stage);
+  constexpr uint32_t idesc = umma::make_idesc_u8(MMA_M, MMA_N, 1, 1);
+  uint32_t uses0 = 0, uses1 = 0;   // commits issued on staging buffer 0 / 1 (uniform over the CTA)
+  bool mma_started = false;        // thread 0: the accumulators hold data
   unsigned long long st_keys = 0, st_dist = 0, st_over = 0;
 
+  // sets owned by this warp
+  const int s_lo = warp * spw;
+  const int s_hi = min(n_sets, s_lo + spw);
+
   const uint32_t n_tiles = *n_tiles_p;
+  // The CTA always holds the tile it works on and the one after it: the key ranges of the
+  // next tile are fetched and its keys are prefetched into L2 while the current tile is built.
+  if (tid == 0) {
+    misc[kMiscTile] = (int)atomicAdd(tile_counter, 1u);
+    misc[kMiscNext] = (int)atomicAdd(tile_counter, 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t t0 = (uint32_t)misc[kMiscTile];
+    if (t0 < n_tiles && tid < NS) {
+      const Tile tl0 = tiles[t0];
+      sbeg[tid] = tid < n_sets ? offsT[(size_t)tl0.x0 * n_sets + tid] : 0u;
+      send[tid] = tid < n_sets ? offsT[(size_t)tl0.x1 * n_sets + tid] : 0u;
+    }
+  }
+  int par = 0;  // which half of sbeg / send holds the current tile
   for (;;) {
-    if (tid == 0) misc[kMiscTile] = (int)atomicAdd(tile_counter, 1u);
     __syncthreads();
     const uint32_t t_id = (uint32_t)misc[kMiscTile];
+    const uint32_t t_nx = (uint32_t)misc[kMiscNext];
     if (t_id >= n_tiles) break;
     const Tile tl = tiles[t_id];
     const uint32_t bucket0 = tl.x0 >> fine_level;
     const int nbk = (int)(((tl.x1 - 1) >> fine_level) - bucket0) + 1;
-    // per-set key ranges of this tile
-    for (int s = tid; s < NPAD; s += T) {
-      uint32_t b = 0, e = 0;
-      if (s < n_sets) {
-        b = offsT[(size_t)tl.x0 * n_sets + s];
-        e = offsT[(size_t)tl.x1 * n_sets + s];
-      }
-      sbeg[s] = b; send[s] = e;
-    }
-    __syncthreads();
-    if (!OWN) {
-      // build work items: segments of kSeg keys; exclusive prefix over sets (NPAD <= T)
-      uint32_t nseg = 0;
-      if (tid < NPAD) nseg = (send[tid] - sbeg[tid] + kSeg - 1) / kSeg;
-      uint32_t inc = nseg;
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (tid < NPAD && lane == 31) misc[kMiscWsum + warp] = (int)inc;
-      __syncthreads();
-      uint32_t woff = 0;
-      if (tid < NPAD)
-        for (int w = 0; w < warp; w++) woff += (uint32_t)misc[kMiscWsum + w];
-      if (tid < NPAD) segpre[tid] = woff + inc - nseg;
-      if (tid == NPAD - 1) misc[kMiscItems] = (int)(woff + inc);
+    const uint32_t* sb = sbeg + par * NS;
+    const uint32_t* se = send + par * NS;
+    // next tile: key ranges into registers now, into shared memory after the build
+    uint32_t nx_b = 0, nx_e = 0;
+    if (t_nx < n_tiles && tid < n_sets) {
+      const Tile tn = tiles[t_nx];
+      // volatile asm: the loads are issued here, not sunk to their use after the build
+      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx_b) : "l"(offsT + (size_t)tn.x0 * n_sets + tid));
+      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx_e) : "l"(offsT + (size_t)tn.x1 * n_sets + tid));
     }
     if (tid == 0) { misc[kMiscSp] = 1; stack[0] = make_uint2(0u, 1u); }  // class (p=0, P=1) = everything
+    bool prefetched = false;
     __syncthreads();
-    const int n_items = misc[kMiscItems];
 
     // process the stack of key classes (normally exactly one entry)
     for (;;) {
@@ -595,60 +520,63 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
       if (tid == 0) misc[kMiscSp] -= 1;
       const uint32_t cp = cls.x, cmask = cls.y - 1u;
 
-      // ---- build -------------------------------------------------------
-#define PROCESS_RUN(S_, BEG_, END_, TOP_) \
-  process_run<KeyT, TK, MW, OWN, UNR>(skeys, smask, order, misc, (const KeyT*)skp[S_], (BEG_), (END_), (TOP_), (S_), lane, cmask, cp)
-      if (OWN) {
-        // warp w owns set groups w, w + NW, ... (8 sets each)
-        const int n_groups = (n_sets + 7) >> 3;
-        for (int g = warp; g < n_groups; g += NW) {
-          const int s_end = min(n_sets, g * 8 + 8);
-          for (int s = g * 8; s < s_end; s++) {
-            if (nbk == 1) {
-              PROCESS_RUN(s, sbeg[s], send[s], (TK)0);
-            } else {
-              for (int b = 0; b < nbk; b++) {
-                const size_t row0 = (size_t)(bucket0 + (uint32_t)b) << fine_level;
-                const uint32_t beg = max(offsT[row0 * n_sets + s], sbeg[s]);
-                const uint32_t end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], send[s]);
-                PROCESS_RUN(s, beg, end, (TK)b << key_bits);
-              }
-            }
-            __syncwarp();
-            if (*(volatile int*)&misc[kMiscOverflow]) break;
+      // ---- build: warp w inserts the keys of its own sets, one set after the other ----------
+      for (int s = s_lo; s < s_hi; s++) {
+        const uint32_t bit = 1u << (s - s_lo);
+        const KeyT* kp = (const KeyT*)skp[s];
+#define PC_RUN(BEG_, END_, TOP_)                                                                              \
+  do {                                                                                                        \
+    if (cmask) process_run<KeyT, TK, NS, UNR, true>(skeys, maskb, misc, kp, (BEG_), (END_), (TOP_), warp, bit, lane, cmask, cp); \
+    else process_run<KeyT, TK, NS, UNR, false>(skeys, maskb, misc, kp, (BEG_), (END_), (TOP_), warp, bit, lane, 0u, 0u);       \
+  } while (0)
+        if (nbk == 1) {
+          PC_RUN(sb[s], se[s], (TK)0);
+        } else {
+          // tile spans several buckets: table key = (bucket - first bucket of the tile) << key_bits | key
+          for (int b = 0; b < nbk; b++) {
+            const size_t row0 = (size_t)(bucket0 + (uint32_t)b) << fine_level;
+            const uint32_t beg = max(offsT[row0 * n_sets + s], sb[s]);
+            const uint32_t end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], se[s]);
+            PC_RUN(beg, end, (TK)b << key_bits);
           }
-          if (*(volatile int*)&misc[kMiscOverflow]) break;
         }
-      } else if (nbk == 1) {
-        // tile inside one bucket: the key alone identifies the k-mer; segments of kSeg keys
-        for (int item = warp; item < n_items; item += NW) {
-          int lo = 0, hi = NPAD - 1;  // set owning this item: largest s with segpre[s] <= item
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (segpre[mid] <= (uint32_t)item) lo = mid; else hi = mid - 1;
-          }
-          const int s = lo;
-          const uint32_t start = sbeg[s] + ((uint32_t)item - segpre[s]) * kSeg;
-          PROCESS_RUN(s, start, min(start + (uint32_t)kSeg, send[s]), (TK)0);
-          if (*(volatile int*)&misc[kMiscOverflow]) break;
-        }
-      } else {
-        // tile spans several buckets: one item per (bucket, set); the table key is
-        // (bucket - first bucket of the tile) << key_bits | key
-        const int n_bitems = nbk * n_sets;
-        for (int item = warp; item < n_bitems; item += NW) {
-          const int b = item / n_sets, s = item - b * n_sets;
-          const size_t row0 = (size_t)(bucket0 + (uint32_t)b) << fine_level;
-          const uint32_t beg = max(offsT[row0 * n_sets + s], sbeg[s]);
-          const uint32_t end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], send[s]);
-          PROCESS_RUN(s, beg, end, (TK)b << key_bits);
-          if (*(volatile int*)&misc[kMiscOverflow]) break;
+#undef PC_RUN
+        __syncwarp();
+        if (*(volatile int*)&misc[kMiscOverflow]) break;
+      }
+      __syncthreads();
+
+      if (!prefetched) {
+        // keys of the next tile -> L2 (one 128-byte line per request), ranges -> shared memory
+        prefetched = true;
+        if (tid < NS) { sbeg[(par ^ 1) * NS + tid] = nx_b; send[(par ^ 1) * NS + tid] = nx_e; }
+        if (tid < n_sets && nx_e > nx_b) {
+          const char* base = (const char*)skp[tid];
+          const size_t lo = ((size_t)nx_b * sizeof(KeyT)) & ~(size_t)127, hi = (size_t)nx_e * sizeof(KeyT);
+          for (size_t off = lo; off < hi; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
         }
       }
-#undef PROCESS_RUN
+
+      // ---- compact: list the occupied slots ----------------------------------------------
+      if (!misc[kMiscOverflow]) {
+        for (int base = warp * 32; base <= S; base += T) {
+          const int slot = base + lane;
+          const bool occ = slot < S ? (skeys[slot] != EMPTY) : (slot == S && sizeof(TK) == 4 && misc[kMiscSpecial] != 0);
+          const unsigned bal = __ballot_sync(0xffffffffu, occ);
+          if (bal) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&misc[kMiscNdist], __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (occ) {
+              const int r = pos + __popc(bal & ((1u << lane) - 1u));
+              if (r < DMAX) list[r] = (uint16_t)slot;
+            }
+          }
+        }
+      }
       __syncthreads();
       const int D = misc[kMiscNdist];
-      if (misc[kMiscOverflow]) {
+      if (misc[kMiscOverflow] || D > DMAX) {
         // too many distinct keys for one pass: wipe the table, split the class in two
         __syncthreads();
         for (int i = tid; i <= S; i += T) skeys[i] = EMPTY;
@@ -671,64 +599,101 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, const uint32_t*
       }
       st_dist += (tid == 0) ? (unsigned long long)D : 0ull;
 
-      // ---- gram, CW * 32 distinct keys per chunk ---------------------------
-      for (int c0 = 0; c0 < D; c0 += kChunkWords * 32) {
-        const int ng = min(kChunkWords, (D - c0 + 31) >> 5);
-        for (int g = warp; g < ng; g += NW) {
-          const int r = c0 + g * 32 + lane;
-          uint32_t m[MW];
-#pragma unroll
-          for (int w = 0; w < MW; w++) m[w] = 0;
+      // ---- gram: CK K-steps (32 distinct keys each) per staging buffer ------------------------
+      for (int c0 = 0; c0 < D; c0 += CK * 32) {
+        const int nk = min(CK, (D - c0 + 31) >> 5);   // K-steps in this chunk
+        const uint32_t nuse = uses0 + uses1;
+        const int buf = (int)(nuse & 1u);
+        const uint32_t used = buf ? uses1 : uses0;
+        // the MMAs that read this buffer two chunks ago must have completed
+        if (used > 0) umma::mbar_wait(&bar[buf], (used - 1) & 1u);
+        unsigned char* sb = stage + (size_t)buf * LY::buf_bytes;
+        // work item = (K-step, mask word): 32 keys x 32 sets -> two 16-set blocks of 16-byte rows
+        for (int item = warp; item < nk * MW; item += NW) {
+          const int ks = item / MW, w = item - ks * MW;
+          const int r = c0 + ks * 32 + lane;
+          uint32_t m = 0;
           if (r < D) {
-            const uint32_t slot = order[r];
-#pragma unroll
-            for (int w = 0; w < MW; w++) { m[w] = smask[slot * MW + w]; smask[slot * MW + w] = 0; }
-            skeys[slot] = EMPTY;
+            const uint32_t slot = list[r];
+            m = smask[slot * MW + w];
+            smask[slot * MW + w] = 0;
+            if (w == 0) skeys[slot] = EMPTY;
           }
-#pragma unroll
-          for (int w = 0; w < MW; w++) colT[g * NPAD + w * 32 + lane] = warp_transpose32(m[w], lane);
+          uint4 lo, hi;
+          lo.x = umma::nibble_to_bytes(m);       lo.y = umma::nibble_to_bytes(m >> 4);
+          lo.z = umma::nibble_to_bytes(m >> 8);  lo.w = umma::nibble_to_bytes(m >> 12);
+          hi.x = umma::nibble_to_bytes(m >> 16); hi.y = umma::nibble_to_bytes(m >> 20);
+          hi.z = umma::nibble_to_bytes(m >> 24); hi.w = umma::nibble_to_bytes(m >> 28);
+          unsigned char* kb = sb + (size_t)ks * LY::kstep_bytes + (size_t)lane * 16;
+          *reinterpret_cast<uint4*>(kb + (size_t)(2 * w) * 512) = lo;
+          *reinterpret_cast<uint4*>(kb + (size_t)(2 * w + 1) * 512) = hi;
         }
+        umma::fence_async_smem();
         __syncthreads();
-#pragma unroll
-        for (int t = 0; t < NBLK; t++) {
-          if (my_bi[t] < 0) continue;
-          const uint4* ca = reinterpret_cast<const uint4*>(colT + my_bi[t] * 4);
-          const uint4* cb = reinterpret_cast<const uint4*>(colT + my_bj[t] * 4);
-          for (int g = 0; g < ng; g++) {
-            const uint4 a = ca[g * (NPAD / 4)];
-            const uint4 b = cb[g * (NPAD / 4)];
-            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
-            const uint32_t bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-              for (int j = 0; j < 4; j++) acc[t][i * 4 + j] += __popc(av[i] & bv[j]);
+        if (tid == 0) {
+          umma::fence_after_thread_sync();
+          const uint32_t a0 = stage_addr + (uint32_t)buf * (uint32_t)LY::buf_bytes;
+          for (int ks = 0; ks < nk; ks++) {
+            const uint32_t a = a0 + (uint32_t)ks * (uint32_t)LY::kstep_bytes;
+            const uint64_t bd = umma::make_smem_desc(a, 128u, 512u);
+            umma::mma_u8(tmem_base, bd, bd, idesc, mma_started ? 1u : 0u);
+            if (NS == 256) {
+              // rows 128..255 of the Gram: A operand starts at set block 8, accumulators at column 256
+              const uint64_t ad = umma::make_smem_desc(a + 8u * 512u, 128u, 512u);
+              umma::mma_u8(tmem_base + 256u, ad, bd, idesc, mma_started ? 1u : 0u);
+            }
+            mma_started = true;
           }
+          umma::mma_commit(&bar[buf]);
+          misc[kMiscAnyMma] = 1;
         }
-        __syncthreads();
+        if (buf) uses1++; else uses0++;
       }
       if (tid == 0) { misc[kMiscNdist] = 0; misc[kMiscSpecial] = 0; }
     }
-    if (tid < NPAD) st_keys += send[tid] - sbeg[tid];
+    if (tid < NS) st_keys += se[tid] - sb[tid];
     __syncthreads();
+    if (tid == 0) {
+      misc[kMiscTile] = misc[kMiscNext];
+      misc[kMiscNext] = (int)atomicAdd(tile_counter, 1u);
+    }
+    par ^= 1;
   }
 
-  // flush accumulators: W is n x n, symmetric
+  // ---- drain the tensor pipe, read the accumulators back, add them to W ----------------------
+  if (uses0 > 0) umma::mbar_wait(&bar[0], (uses0 - 1) & 1u);
+  if (uses1 > 0) umma::mbar_wait(&bar[1], (uses1 - 1) & 1u);
+  umma::fence_after_thread_sync();
+  __syncthreads();
+  if (misc[kMiscAnyMma] && warp < 4) {
+    // warp q reads TMEM lanes 32 q .. 32 q + 31. M = 64: row m lives in lane (m % 16) + 32 (m / 16);
+    // M = 128: row m in lane m (rows 128.. of NS = 256 in columns 256..511).
+    constexpr int HALVES = NS == 256 ? 2 : 1;
+#pragma unroll 1
+    for (int half = 0; half < HALVES; half++) {
+      int row;
+      if (NS == 64) row = lane < 16 ? warp * 16 + lane : -1;
+      else row = half * 128 + warp * 32 + lane;
+      const int si = row >= 0 ? set_of_pos(row, spw, n_sets) : -1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < MMA_N; c0 += 32) {
+        uint32_t v[32];
+        umma::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 256 + c0), v);
+        umma::tmem_ld_wait();
+        if (si >= 0) {
 #pragma unroll
-  for (int t = 0; t < NBLK; t++) {
-    if (my_bi[t] < 0) continue;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int si = my_bi[t] * 4 + i, sj = my_bj[t] * 4 + j;
-        const uint32_t v = acc[t][i * 4 + j];
-        if (si >= n_sets || sj >= n_sets || v == 0) continue;
-        atomicAdd(&W[(size_t)si * n_sets + sj], (unsigned long long)v);
-        // a diagonal block holds both (i,j) and (j,i) already
-        if (my_bi[t] != my_bj[t]) atomicAdd(&W[(size_t)sj * n_sets + si], (unsigned long long)v);
+          for (int j = 0; j < 32; j++) {
+            const int sj = set_of_pos(c0 + j, spw, n_sets);
+            if (sj >= 0 && v[j] != 0) atomicAdd(&W[(size_t)si * n_sets + sj], (unsigned long long)v[j]);
+          }
+        }
       }
+    }
   }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, TMEM_COLS);
+
   // stats: keys processed, distinct keys, overflow retries
   for (int o = 16; o > 0; o >>= 1) st_keys += __shfl_xor_sync(0xffffffffu, st_keys, o);
   if (lane == 0 && st_keys) atomicAdd(&stats[0], st_keys);
@@ -777,43 +742,69 @@ __global__ void pair_counts_merge_kernel(const SetDesc* __restrict__ sets, int n
 // host side
 // ---------------------------------------------------------------------------
 
-template <typename KeyT, int MW>
+template <typename KeyT, int NS>
 static int launch_main(kmsc_ctx* ctx, const SetDesc* d_sets, int n_sets, const uint32_t* d_offsT,
                        const Tile* d_tiles, const uint32_t* d_ntiles, uint32_t* d_counter,
                        unsigned long long* d_W, unsigned long long* d_stats, int key_bits, int fine_level,
                        uint32_t max_tiles) {
   using TK = typename TableKey<KeyT>::type;
-  const size_t smem = PcSmem<MW>::bytes((int)sizeof(TK));
-  auto kern = pair_counts_kernel<KeyT, MW>;
-  KMSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  KMSC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PcCfg<MW>::T, smem));
-  if (occ < 1) { set_error("pair_counts kernel does not fit on an SM (smem %zu)", smem); return KMSC_E_CUDA; }
+  using C = PcCfg<NS, (int)sizeof(TK)>;
+  const size_t smem = PcSmem<NS>::bytes((int)sizeof(TK));
+  auto kern = pair_counts_kernel<KeyT, NS>;
+  // Resident CTAs per SM from the kernel's own resources. (The occupancy API answers 1 for
+  // any kernel that allocates tensor memory, whatever the column count.) Every resident CTA
+  // holds its accumulators in TMEM: 512 columns per SM bound the count as well. Computed once
+  // per instantiation and device.
+  static int occ_cache[64] = {0};
+  int occ = ctx->device < 64 ? occ_cache[ctx->device] : 0;
+  if (occ == 0) {
+    KMSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    KMSC_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int smem_sm = 0, smem_res = 0, regs_sm = 0, thr_sm = 0;
+    KMSC_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, ctx->device));
+    const int tmem_cols = NS == 256 ? 512 : NS;
+    occ = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + (size_t)smem_res));
+    const int regs_per_cta = ((fa.numRegs + 7) & ~7) * C::T;
+    if (regs_per_cta > 0) occ = std::min(occ, regs_sm / regs_per_cta);
+    occ = std::min(occ, thr_sm / C::T);
+    occ = std::min(occ, 512 / tmem_cols);
+    if (occ < 1) { set_error("pair_counts kernel does not fit on an SM (smem %zu, %d regs)", smem, fa.numRegs); return KMSC_E_CUDA; }
+    if (getenv("KMSC_DEBUG"))
+      fprintf(stderr, "[kmsc] pair_counts NS=%d T=%d smem=%zu regs=%d -> %d CTAs per SM\n", NS, C::T, smem, fa.numRegs, occ);
+    if (ctx->device < 64) occ_cache[ctx->device] = occ;
+  }
   long long grid = (long long)ctx->sm_count * occ;
   if (grid > (long long)max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, PcCfg<MW>::T, smem, ctx->stream>>>(d_sets, n_sets, d_offsT, d_tiles, d_ntiles,
-                                                            d_counter, d_W, d_stats, key_bits, fine_level);
+  const int n_warps = C::T / 32;
+  const int spw = (n_sets + n_warps - 1) / n_warps;  // sets per warp (<= 8)
+  kern<<<(unsigned)grid, C::T, smem, ctx->stream>>>(d_sets, n_sets, spw, d_offsT, d_tiles, d_ntiles,
+                                                    d_counter, d_W, d_stats, key_bits, fine_level);
   count_launch(ctx);
   KMSC_CUDA(cudaGetLastError());
   return KMSC_OK;
 }
 
 template <typename KeyT>
-static int launch_main_mw(kmsc_ctx* ctx, int mw, const SetDesc* d_sets, int n_sets,
+static int launch_main_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_sets,
                           const uint32_t* d_offsT, const Tile* d_tiles, const uint32_t* d_ntiles,
                           uint32_t* d_counter, unsigned long long* d_W, unsigned long long* d_stats,
                           int key_bits, int fine_level, uint32_t max_tiles) {
-  switch (mw) {
-    case 1: return launch_main<KeyT, 1>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
-    case 2: return launch_main<KeyT, 2>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
-    case 4: return launch_main<KeyT, 4>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
-    default: return launch_main<KeyT, 8>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
+  switch (ns) {
+    case 64: return launch_main<KeyT, 64>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
+    case 128: return launch_main<KeyT, 128>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
+    default: return launch_main<KeyT, 256>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
   }
 }
 
-static int dmax_for(int mw) {
-  switch (mw) { case 1: return PcCfg<1>::D; case 2: return PcCfg<2>::D; case 4: return PcCfg<4>::D; default: return PcCfg<8>::D; }
+static int dmax_for(int ns, int tk_bytes) {
+  if (ns == 64) return PcCfg<64, 4>::D;
+  if (ns == 128) return PcCfg<128, 4>::D;
+  return tk_bytes == 8 ? PcCfg<256, 8>::D : PcCfg<256, 4>::D;
 }
 
 // device-side small block layout (ctx->small):
@@ -826,7 +817,7 @@ struct PcDev {
 
 // One pass: plan tiles over the buckets selected by h_bitmap (NULL = all) with
 // tile target L, then run the main kernel accumulating into d_W.
-static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int mw,
+static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
                      const uint32_t* h_bitmap, unsigned long long L, double keys_in_phase,
                      unsigned long long* d_W, unsigned long long host_stats[4]) {
   const kmsc_set* s0 = sets[0];
@@ -900,9 +891,9 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int mw,
   KMSC_CUDA(cudaEventRecord(ctx->pc_ev[1], ctx->stream));
   int rc;
   switch (s0->key_bytes) {
-    case 2: rc = launch_main_mw<uint16_t>(ctx, mw, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
-    case 4: rc = launch_main_mw<uint32_t>(ctx, mw, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
-    default: rc = launch_main_mw<unsigned long long>(ctx, mw, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
+    case 2: rc = launch_main_ns<uint16_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
+    case 4: rc = launch_main_ns<uint32_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
+    default: rc = launch_main_ns<unsigned long long>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
   }
   if (rc != KMSC_OK) return rc;
   KMSC_CUDA(cudaEventRecord(ctx->pc_ev[2], ctx->stream));
@@ -998,8 +989,8 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
     return KMSC_OK;
   }
 
-  const int mw = n <= 32 ? 1 : n <= 64 ? 2 : n <= 128 ? 4 : 8;
-  const int dmax = dmax_for(mw);
+  const int ns = n <= 64 ? 64 : n <= 128 ? 128 : 256;  // rows of the tensor-core Gram
+  const int dmax = dmax_for(ns, s0->key_bytes == 8 ? 8 : 4);
   const unsigned long long L_cons = (unsigned long long)(0.75 * dmax);
   const unsigned long long L_max = 1ull << 20;
   const double mean_bucket = (double)total_keys / (double)nb;  // all sets, per bucket
@@ -1020,7 +1011,7 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
       if ((rank++ & 63) == 21) probe[b >> 5] |= 1u << (b & 31);
       else rest[b >> 5] |= 1u << (b & 31);
     }
-    KMSC_TRY(run_phase(ctx, sets, n, mw, probe.data(), L_cons, mean_bucket, d_W, st));
+    KMSC_TRY(run_phase(ctx, sets, n, ns, probe.data(), L_cons, mean_bucket, d_W, st));
     if (st[1] > 0) rho = (double)st[0] / (double)st[1];
     ctx->pc_last_stats[0] += st[0]; ctx->pc_last_stats[1] += st[1]; ctx->pc_last_stats[2] += st[2];
     phase2 = rest.data();
@@ -1031,7 +1022,7 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
     if (La > L) L = La;
   }
   if (L > L_max) L = L_max;
-  KMSC_TRY(run_phase(ctx, sets, n, mw, phase2, L, mean_bucket, d_W, st));
+  KMSC_TRY(run_phase(ctx, sets, n, ns, phase2, L, mean_bucket, d_W, st));
   if (st[1] > 0) {
     ctx->pc_rho = (double)st[0] / (double)st[1];
     ctx->pc_rho_n = n;
