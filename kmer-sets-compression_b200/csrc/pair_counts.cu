@@ -274,7 +274,7 @@ struct PcLayout {
 
 // misc[] slots
 constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscSp = 3, kMiscSpecial = 4, kMiscTmem = 5,
-              kMiscAnyMma = 6, kMiscNext = 7;
+              kMiscAnyMma = 6, kMiscNext = 7, kMiscIns = 8;
 
 // The table is probed two slots at a time: slots (h, h + 1) with h even are one 8 / 16-byte
 // load. Slow path, per lane (divergent, rare): neither slot of the home pair held the key
@@ -282,13 +282,14 @@ constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscSp = 3, kMi
 // sequence longer than the table means the table is full: flag overflow (the pass is
 // repeated on a split class).
 template <typename TK, int S>
-__device__ __forceinline__ uint32_t find_slot_slow(TK* skeys, int* misc, TK key, uint32_t h) {
+__device__ __forceinline__ uint32_t find_slot_slow(TK* skeys, int* misc, TK key, uint32_t h, uint32_t& n_new) {
   const TK EMPTY = (TK)~(TK)0;
   for (int n = 0; n <= S; n++) {
     const TK c = skeys[h];
     if (c == key) return h;
     if (c == EMPTY) {
       const TK old = atomicCAS(&skeys[h], EMPTY, key);
+      if (old == EMPTY) n_new += 1;
       if (old == EMPTY || old == key) return h;
     }
     h = (h + 1) & (S - 1);
@@ -311,46 +312,63 @@ template <> struct SlotPair<unsigned long long> {
   }
 };
 
-// Insert keys [i0, i0 + 32 U) of one set (table key = top | key) and set bit `bit` of the mask
-// byte `byte_idx` this warp owns. U rows of 32 keys are handled as a batch: U independent
-// coalesced global loads, U independent pair probes, claims of empty slots, the rare slow
-// paths, U marks. The keys of one set are distinct, so the U marks of a batch never hit the
-// same byte. CLS: only keys of hash class (cmask, cp) take part (after a table overflow).
-template <typename KeyT, typename TK, int NS, int U, bool FULL, bool CLS>
-__device__ __forceinline__ void process_batch(TK* skeys, uint8_t* maskb, int* misc, const KeyT* __restrict__ kp,
-                                              uint32_t i0, uint32_t end, TK top, int byte_idx, uint32_t bit,
-                                              int lane, uint32_t cmask, uint32_t cp) {
-  using C = PcCfg<NS, (int)sizeof(TK)>;
-  constexpr int MWB = NS / 8;  // mask bytes per slot
-  const TK EMPTY = (TK)~(TK)0;
-  KeyT kk[U];
+// One batch of the build: U rows of 32 keys of ONE set (rows past `end` are masked off).
+struct PcBatch {
+  const void* kp;   // keys of the set
+  uint32_t i0, end; // key indices [i0, min(i0 + 32 U, end))
+  uint32_t bit;     // membership bit inside the mask byte this warp owns
+};
+
+template <typename KeyT, int U>
+__device__ __forceinline__ void batch_load(const PcBatch& b, int lane, KeyT (&kk)[U]) {
+  const KeyT* kp = (const KeyT*)b.kp;
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    const uint32_t i = i0 + u * 32 + lane;
-    kk[u] = (FULL || i < end) ? __ldg(kp + i) : (KeyT)0;
+    const uint32_t i = b.i0 + u * 32 + lane;
+    kk[u] = i < b.end ? __ldg(kp + i) : (KeyT)0;
   }
+}
+
+// Insert the keys of a batch (table key = top | key) and set the batch's membership bit in
+// the mask byte at byte offset `mbase + 4 * slot` (masks are stored as word planes:
+// word w of slot s at smask[w * (S + 1) + s], so a warp's byte accesses spread over all 32
+// banks). U independent pair probes, claims of empty slots, the rare slow paths, U marks.
+// The keys of one set are distinct, so the U marks of a batch never hit the same byte.
+// cmask != 0: only keys of hash class (cmask, cp) take part (after a table overflow).
+template <typename KeyT, typename TK, int NS, int U>
+__device__ __forceinline__ void batch_process(TK* skeys, uint8_t* maskb, int* misc, const PcBatch& b, const KeyT (&kk)[U],
+                                              TK top, uint32_t mbase, int lane, uint32_t cmask, uint32_t cp,
+                                              uint32_t& w_new) {
+  using C = PcCfg<NS, (int)sizeof(TK)>;
+  const TK EMPTY = (TK)~(TK)0;
   TK key[U], c0[U], c1[U];
   uint32_t h[U];
   bool act[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    const uint32_t i = i0 + u * 32 + lane;
     key[u] = top | (TK)kk[u];
-    act[u] = FULL || i < end;
-    if (CLS) act[u] = act[u] && (hash_class(key[u]) & cmask) == cp;
+    act[u] = b.i0 + u * 32 + lane < b.end;
     h[u] = hash_slot(key[u], C::LOG2S) & ~1u;
+  }
+  if (cmask) {
+#pragma unroll
+    for (int u = 0; u < U; u++) act[u] = act[u] && (hash_class(key[u]) & cmask) == cp;
   }
 #pragma unroll
   for (int u = 0; u < U; u++) SlotPair<TK>::load(&skeys[h[u]], c0[u], c1[u]);
+  bool any_sp = false;
+  uint32_t n_new = 0;  // slots this lane claimed
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    bool pend = act[u] && c0[u] != key[u];
-    if (c1[u] == key[u]) { h[u] += 1; pend = false; }
-    if (sizeof(TK) == 4 && key[u] == EMPTY) {
+    const bool hit1 = c1[u] == key[u];
+    bool pend = act[u] && c0[u] != key[u] && !hit1;
+    h[u] += hit1 ? 1u : 0u;
+    if (sizeof(TK) == 4) {
       // the one key that collides with the empty marker lives in the extra slot S
-      if (act[u]) misc[kMiscSpecial] = 1;
-      h[u] = C::S;
-      pend = false;
+      const bool sp = key[u] == EMPTY;
+      h[u] = sp ? (uint32_t)C::S : h[u];
+      pend = pend && !sp;
+      any_sp |= sp && act[u];
     }
     if (pend) {
       // new key (or a collision): claim the first empty slot of the pair
@@ -359,43 +377,33 @@ __device__ __forceinline__ void process_batch(TK* skeys, uint8_t* maskb, int* mi
       if (c0[u] == EMPTY) {
         const TK old = atomicCAS(&skeys[hh], EMPTY, key[u]);
         done = (old == EMPTY) || (old == key[u]);
+        n_new += old == EMPTY;
       }
       if (!done && c1[u] == EMPTY) {
         hh += 1;
         const TK old = atomicCAS(&skeys[hh], EMPTY, key[u]);
         done = (old == EMPTY) || (old == key[u]);
+        n_new += old == EMPTY;
       }
-      if (!done) hh = find_slot_slow<TK, C::S>(skeys, misc, key[u], h[u]);
+      if (!done) hh = find_slot_slow<TK, C::S>(skeys, misc, key[u], (h[u] + 2) & (C::S - 1), n_new);
       h[u] = hh;
     }
   }
+  if (sizeof(TK) == 4 && any_sp) misc[kMiscSpecial] = 1;
+  // early overflow check: the distinct keys of this pass must fit D slots (a nearly full
+  // table makes every probe sequence long well before it is completely full). Claims are
+  // summed per warp and published in lumps of >= 64.
+  w_new += __reduce_add_sync(0xffffffffu, n_new);
+  if (w_new >= 64) {
+    if (lane == 0 && atomicAdd(&misc[kMiscIns], (int)w_new) + (int)w_new > C::D) misc[kMiscOverflow] = 1;
+    w_new = 0;
+  }
   uint8_t mv[U];
 #pragma unroll
-  for (int u = 0; u < U; u++) mv[u] = maskb[h[u] * MWB + byte_idx];
+  for (int u = 0; u < U; u++) mv[u] = maskb[mbase + h[u] * 4];
 #pragma unroll
   for (int u = 0; u < U; u++)
-    if (act[u]) maskb[h[u] * MWB + byte_idx] = (uint8_t)(mv[u] | bit);
-}
-
-template <typename KeyT, typename TK, int NS, int UNR, bool CLS>
-__device__ __forceinline__ void process_run(TK* skeys, uint8_t* maskb, int* misc, const KeyT* __restrict__ kp,
-                                            uint32_t beg, uint32_t end, TK top, int byte_idx, uint32_t bit,
-                                            int lane, uint32_t cmask, uint32_t cp) {
-  uint32_t i0 = beg;
-  // full batches: no bounds checks
-  for (; i0 + 32 * UNR <= end; i0 += 32 * UNR) {
-    process_batch<KeyT, TK, NS, UNR, true, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
-    if (*(volatile int*)&misc[kMiscOverflow]) return;
-  }
-  if (i0 >= end) return;
-  // tail: 1 .. UNR - 1 full rows and possibly a partial one, as one bounds-checked batch
-  const uint32_t rows = (end - i0 + 31) >> 5;
-  if (UNR >= 4 && rows > 2)
-    process_batch<KeyT, TK, NS, UNR, false, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
-  else if (UNR >= 2 && rows == 2)
-    process_batch<KeyT, TK, NS, 2, false, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
-  else
-    process_batch<KeyT, TK, NS, 1, false, CLS>(skeys, maskb, misc, kp, i0, end, top, byte_idx, bit, lane, cmask, cp);
+    if (act[u]) maskb[mbase + h[u] * 4] = (uint8_t)(mv[u] | b.bit);
 }
 
 template <int NS>
@@ -452,7 +460,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
   for (int i = tid; i < (S + 1) * MW; i += T) smask[i] = 0;
   for (int i = tid; i < NS; i += T) skp[i] = i < n_sets ? sets[i].keys : nullptr;
   if (tid == 0) {
-    misc[kMiscNdist] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0; misc[kMiscAnyMma] = 0;
+    misc[kMiscNdist] = 0; misc[kMiscIns] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0; misc[kMiscAnyMma] = 0;
     umma::mbar_init(&bar[0], 1);
     umma::mbar_init(&bar[1], 1);
     umma::mbar_fence_init();
@@ -468,6 +476,8 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
   bool mma_started = false;        // thread 0: the accumulators hold data
   unsigned long long st_keys = 0, st_dist = 0, st_over = 0;
 
+  // byte offset of the mask byte this warp owns in slot 0 (word plane warp / 4, byte warp % 4)
+  const uint32_t mbase = (uint32_t)(warp >> 2) * (uint32_t)(S + 1) * 4u + (uint32_t)(warp & 3);
   // sets owned by this warp
   const int s_lo = warp * spw;
   const int s_hi = min(n_sets, s_lo + spw);
@@ -512,38 +522,74 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
     __syncthreads();
 
     // process the stack of key classes (normally exactly one entry)
-    for (;;) {
+    for (uint32_t n_pass = 0;; n_pass++) {
       __syncthreads();
       if (misc[kMiscSp] == 0) break;
+      if (n_pass > (1u << 20)) {  // watchdog
+        if (tid == 0) { atomicAdd(&stats[3], 1ull); atomicOr(&stats[4], 4ull); }
+        break;
+      }
       const uint2 cls = stack[misc[kMiscSp] - 1];
       __syncthreads();
       if (tid == 0) misc[kMiscSp] -= 1;
       const uint32_t cp = cls.x, cmask = cls.y - 1u;
 
-      // ---- build: warp w inserts the keys of its own sets, one set after the other ----------
-      for (int s = s_lo; s < s_hi; s++) {
-        const uint32_t bit = 1u << (s - s_lo);
-        const KeyT* kp = (const KeyT*)skp[s];
-#define PC_RUN(BEG_, END_, TOP_)                                                                              \
-  do {                                                                                                        \
-    if (cmask) process_run<KeyT, TK, NS, UNR, true>(skeys, maskb, misc, kp, (BEG_), (END_), (TOP_), warp, bit, lane, cmask, cp); \
-    else process_run<KeyT, TK, NS, UNR, false>(skeys, maskb, misc, kp, (BEG_), (END_), (TOP_), warp, bit, lane, 0u, 0u);       \
-  } while (0)
-        if (nbk == 1) {
-          PC_RUN(sb[s], se[s], (TK)0);
-        } else {
-          // tile spans several buckets: table key = (bucket - first bucket of the tile) << key_bits | key
+      // ---- build: warp w inserts the keys of its own sets, one set after the other. The
+      // keys of batch i + 1 (possibly of the next set) are loaded before batch i is probed.
+      uint32_t w_new = 0;  // slots claimed by this warp, not yet published
+      if (nbk == 1) {
+        PcBatch cur, nxt;
+        KeyT ck[UNR], nk[UNR];
+        int s = s_lo;
+        auto first_of = [&](int from, PcBatch& o) -> int {  // first non-empty set >= from
+          int t = from;
+          while (t < s_hi && se[t] <= sb[t]) t++;
+          if (t < s_hi) { o.kp = skp[t]; o.i0 = sb[t]; o.end = se[t]; o.bit = 1u << (t - s_lo); }
+          return t;
+        };
+        s = first_of(s_lo, cur);
+        bool have = s < s_hi;
+        if (have) batch_load<KeyT, UNR>(cur, lane, ck);
+        while (have) {
+          // successor: next rows of the same set, else the first rows of the next set
+          bool hn;
+          bool new_set = false;
+          if (cur.i0 + 32 * UNR < cur.end) {
+            nxt = cur; nxt.i0 = cur.i0 + 32 * UNR; hn = true;
+          } else {
+            s = first_of(s + 1, nxt);
+            hn = s < s_hi;
+            new_set = true;
+          }
+          if (hn) batch_load<KeyT, UNR>(nxt, lane, nk);
+          batch_process<KeyT, TK, NS, UNR>(skeys, maskb, misc, cur, ck, (TK)0, mbase, lane, cmask, cp, w_new);
+          if (new_set) __syncwarp();  // marks of different sets may hit the same byte
+          if (*(volatile int*)&misc[kMiscOverflow]) break;
+          cur = nxt;
+#pragma unroll
+          for (int u = 0; u < UNR; u++) ck[u] = nk[u];
+          have = hn;
+        }
+      } else {
+        // tile spans several (small) buckets: table key = (bucket - first bucket of the tile) << key_bits | key
+        for (int s = s_lo; s < s_hi; s++) {
           for (int b = 0; b < nbk; b++) {
             const size_t row0 = (size_t)(bucket0 + (uint32_t)b) << fine_level;
-            const uint32_t beg = max(offsT[row0 * n_sets + s], sb[s]);
-            const uint32_t end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], se[s]);
-            PC_RUN(beg, end, (TK)b << key_bits);
+            PcBatch cur;
+            cur.kp = skp[s];
+            cur.bit = 1u << (s - s_lo);
+            cur.end = min(offsT[(row0 + ((size_t)1 << fine_level)) * n_sets + s], se[s]);
+            for (cur.i0 = max(offsT[row0 * n_sets + s], sb[s]); cur.i0 < cur.end; cur.i0 += 32 * UNR) {
+              KeyT ck[UNR];
+              batch_load<KeyT, UNR>(cur, lane, ck);
+              batch_process<KeyT, TK, NS, UNR>(skeys, maskb, misc, cur, ck, (TK)b << key_bits, mbase, lane, cmask, cp, w_new);
+            }
           }
+          __syncwarp();
+          if (*(volatile int*)&misc[kMiscOverflow]) break;
         }
-#undef PC_RUN
-        __syncwarp();
-        if (*(volatile int*)&misc[kMiscOverflow]) break;
       }
+      if (w_new && lane == 0 && atomicAdd(&misc[kMiscIns], (int)w_new) + (int)w_new > C::D) misc[kMiscOverflow] = 1;
       __syncthreads();
 
       if (!prefetched) {
@@ -582,7 +628,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
         for (int i = tid; i <= S; i += T) skeys[i] = EMPTY;
         for (int i = tid; i < (S + 1) * MW; i += T) smask[i] = 0;
         if (tid == 0) {
-          misc[kMiscNdist] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0;
+          misc[kMiscNdist] = 0; misc[kMiscIns] = 0; misc[kMiscOverflow] = 0; misc[kMiscSpecial] = 0;
           const uint32_t P = cls.y;
           if (misc[kMiscSp] + 2 <= kStackMax && P < 0x40000000u) {
             stack[misc[kMiscSp]] = make_uint2(cp, P * 2);
@@ -606,7 +652,9 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
         const int buf = (int)(nuse & 1u);
         const uint32_t used = buf ? uses1 : uses0;
         // the MMAs that read this buffer two chunks ago must have completed
-        if (used > 0) umma::mbar_wait(&bar[buf], (used - 1) & 1u);
+        if (used > 0 && !umma::mbar_wait_bounded(&bar[buf], (used - 1) & 1u)) {
+          if (lane == 0) { atomicAdd(&stats[3], 1ull); atomicOr(&stats[4], 1ull); }
+        }
         unsigned char* sb = stage + (size_t)buf * LY::buf_bytes;
         // work item = (K-step, mask word): 32 keys x 32 sets -> two 16-set blocks of 16-byte rows
         for (int item = warp; item < nk * MW; item += NW) {
@@ -615,8 +663,8 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
           uint32_t m = 0;
           if (r < D) {
             const uint32_t slot = list[r];
-            m = smask[slot * MW + w];
-            smask[slot * MW + w] = 0;
+            m = smask[w * (S + 1) + slot];
+            smask[w * (S + 1) + slot] = 0;
             if (w == 0) skeys[slot] = EMPTY;
           }
           uint4 lo, hi;
@@ -649,7 +697,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
         }
         if (buf) uses1++; else uses0++;
       }
-      if (tid == 0) { misc[kMiscNdist] = 0; misc[kMiscSpecial] = 0; }
+      if (tid == 0) { misc[kMiscNdist] = 0; misc[kMiscIns] = 0; misc[kMiscSpecial] = 0; }
     }
     if (tid < NS) st_keys += se[tid] - sb[tid];
     __syncthreads();
@@ -661,8 +709,10 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
   }
 
   // ---- drain the tensor pipe, read the accumulators back, add them to W ----------------------
-  if (uses0 > 0) umma::mbar_wait(&bar[0], (uses0 - 1) & 1u);
-  if (uses1 > 0) umma::mbar_wait(&bar[1], (uses1 - 1) & 1u);
+  if ((uses0 > 0 && !umma::mbar_wait_bounded(&bar[0], (uses0 - 1) & 1u)) ||
+      (uses1 > 0 && !umma::mbar_wait_bounded(&bar[1], (uses1 - 1) & 1u))) {
+    if (lane == 0) { atomicAdd(&stats[3], 1ull); atomicOr(&stats[4], 2ull); }
+  }
   umma::fence_after_thread_sync();
   __syncthreads();
   if (misc[kMiscAnyMma] && warp < 4) {
@@ -899,7 +949,7 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
   KMSC_CUDA(cudaEventRecord(ctx->pc_ev[2], ctx->stream));
   // stats come back through pinned memory; the sync also protects the staging buffer
   unsigned long long* h_stats = (unsigned long long*)((unsigned char*)pin + sz_desc + sz_bitmap);
-  KMSC_CUDA(cudaMemcpyAsync(h_stats, d.stats, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaMemcpyAsync(h_stats, d.stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
   KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 4; i++) host_stats[i] = h_stats[i];
   {
@@ -913,7 +963,10 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
     // folded into (NF+1)*n*4 offsets + the n*n*8 result
     ctx->pc_algo_bytes += (double)h_stats[0] * s0->key_bytes + (double)(nb + 1) * n * 4.0;
   }
-  if (host_stats[3]) { set_error("pair_counts: a tile could not be split further (%llu failures)", host_stats[3]); return KMSC_E_STATE; }
+  if (host_stats[3]) {
+    set_error("pair_counts: %llu failures (tile could not be split further, or watchdog code %llu)", host_stats[3], h_stats[4]);
+    return KMSC_E_STATE;
+  }
   return KMSC_OK;
 }
 

@@ -70,6 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// bounded wait (a watchdog against protocol bugs): false if the phase did not complete
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t max_tries = 1u << 18) {
+  for (uint32_t i = 0; i < max_tries; i++)
+    if (mbar_try_wait(bar, parity)) return true;
+  return false;
+}
 
 // ---- descriptors ------------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle; lbo / sbo in bytes (multiples of 16)
