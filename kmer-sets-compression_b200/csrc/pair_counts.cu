@@ -228,7 +228,16 @@ template <> struct TableKey<unsigned long long> { using type = unsigned long lon
 //   S slots, D = max distinct keys per pass, T threads (one warp per 8 sets),
 //   CK = K-steps (32 keys) per staging buffer, UNR = key rows in flight per warp.
 template <int NS, int TKB> struct PcCfg;
-template <int TKB> struct PcCfg<64, TKB>  { static constexpr int S = 4096, LOG2S = 12, D = 2560, T = 256,  CK = 4, UNR = 4, MINB = 3; };
+#ifndef PC_D64
+#define PC_D64 2560
+#endif
+#ifndef PC_UNR64
+#define PC_UNR64 4
+#endif
+#ifndef PC_LFRAC
+#define PC_LFRAC 0.55
+#endif
+template <int TKB> struct PcCfg<64, TKB>  { static constexpr int S = 4096, LOG2S = 12, D = PC_D64, T = 256,  CK = 4, UNR = PC_UNR64, MINB = 3; };
 template <int TKB> struct PcCfg<128, TKB> { static constexpr int S = 2048, LOG2S = 11, D = 1280, T = 512,  CK = 4, UNR = 4, MINB = 2; };
 template <> struct PcCfg<256, 4>          { static constexpr int S = 4096, LOG2S = 12, D = 2560, T = 1024, CK = 4, UNR = 2, MINB = 1; };
 template <> struct PcCfg<256, 8>          { static constexpr int S = 2048, LOG2S = 11, D = 1280, T = 1024, CK = 4, UNR = 2, MINB = 1; };
@@ -1071,7 +1080,7 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
   }
   unsigned long long L = L_cons;
   if (rho > 1.0) {
-    const unsigned long long La = (unsigned long long)(0.55 * rho * dmax);
+    const unsigned long long La = (unsigned long long)(PC_LFRAC * rho * dmax);
     if (La > L) L = La;
   }
   if (L > L_max) L = L_max;

@@ -8,6 +8,123 @@
 #include <stdlib.h>
 #include <string.h>
 
+
+/* ------------------------------------------------------------------------- */
+/* P6: "KMSC" container = delta + streamvbyte-style 1/2/3/4-byte codes        */
+/* ------------------------------------------------------------------------- */
+/* No counterpart in the reference (it never serialises a binary k-mer set); the byte-code
+ * scheme is the one KmerSetCompact applies to its string lengths
+ * (lib/core/kmer_set_compact.h:256-266: control bytes first, 2-bit codes LSB first,
+ * little-endian data bytes), here with the classic 1/2/3/4-byte code lengths. Layout in
+ * kmer-sets-compression_b200/csrc/codec.cu. Checks the GPU codec byte for byte. */
+
+static uint32_t codec_code(uint32_t v) { return v < (1u << 8) ? 0u : v < (1u << 16) ? 1u : v < (1u << 24) ? 2u : 3u; }
+
+/* values -> ctrl (ceil(m/4) bytes) + data; returns data bytes */
+static size_t codec_stream_encode(const uint32_t* v, uint64_t m, uint8_t* ctrl, uint8_t* data) {
+  size_t w = 0;
+  memset(ctrl, 0, (size_t)((m + 3) / 4));
+  for (uint64_t i = 0; i < m; i++) {
+    const uint32_t c = codec_code(v[i]);
+    ctrl[i >> 2] |= (uint8_t)(c << (2 * (i & 3)));
+    for (uint32_t t = 0; t <= c; t++) data[w++] = (uint8_t)(v[i] >> (8 * t));
+  }
+  return w;
+}
+
+static int codec_stream_decode(const uint8_t* ctrl, const uint8_t* data, size_t n_data, uint64_t m, uint32_t* v) {
+  size_t r = 0;
+  for (uint64_t i = 0; i < m; i++) {
+    const uint32_t len = ((ctrl[i >> 2] >> (2 * (i & 3))) & 3u) + 1;
+    if (r + len > n_data) return -1;
+    uint32_t x = 0;
+    for (uint32_t t = 0; t < len; t++) x |= (uint32_t)data[r + t] << (8 * t);
+    v[i] = x;
+    r += len;
+  }
+  return r == n_data ? 0 : -1;
+}
+
+/* CSR (offs int64[2^N + 1], keys of key_bytes each) -> malloc'd container */
+uint8_t* kmsc_o_codec_encode(int K, int N, int key_bytes, const int64_t* offs, const void* keys, int64_t* n_bytes) {
+  const uint64_t nb = (uint64_t)1 << N;
+  const uint64_t n = (uint64_t)offs[nb];
+  const int wpk = key_bytes == 8 ? 2 : 1;
+  const uint64_t m = n * (uint64_t)wpk;
+  uint32_t* sv = (uint32_t*)malloc((size_t)(nb + 1) * 4);
+  uint32_t* kv = (uint32_t*)malloc((size_t)(m + 1) * 4);
+  for (uint64_t b = 0; b < nb; b++) sv[b] = (uint32_t)(offs[b + 1] - offs[b]);
+  for (uint64_t b = 0; b < nb; b++) {
+    uint64_t prev = 0;
+    for (int64_t i = offs[b]; i < offs[b + 1]; i++) {
+      uint64_t k = key_bytes == 2 ? ((const uint16_t*)keys)[i] : key_bytes == 4 ? ((const uint32_t*)keys)[i] : ((const uint64_t*)keys)[i];
+      const uint64_t d = k - prev;
+      prev = k;
+      kv[(uint64_t)i * wpk] = (uint32_t)d;
+      if (wpk == 2) kv[(uint64_t)i * wpk + 1] = (uint32_t)(d >> 32);
+    }
+  }
+  const size_t cap = 48 + (size_t)(nb + 3) / 4 + (size_t)nb * 4 + (size_t)(m + 3) / 4 + (size_t)m * 4 + 16;
+  uint8_t* out = (uint8_t*)malloc(cap);
+  size_t w = 48;
+  const size_t n_sctrl = (size_t)(nb + 3) / 4;
+  const size_t n_sdata = codec_stream_encode(sv, nb, out + w, out + w + n_sctrl);
+  w += n_sctrl + n_sdata;
+  const size_t n_kctrl = (size_t)(m + 3) / 4;
+  const size_t n_kdata = codec_stream_encode(kv, m, out + w, out + w + n_kctrl);
+  w += n_kctrl + n_kdata;
+  const uint32_t h32[6] = {0x43534D4Bu, 1u, (uint32_t)K, (uint32_t)N, (uint32_t)key_bytes, (uint32_t)wpk};
+  const uint64_t h64[3] = {n, (uint64_t)n_sdata, (uint64_t)n_kdata};
+  memcpy(out, h32, 24);
+  memcpy(out + 24, h64, 24);
+  free(sv); free(kv);
+  *n_bytes = (int64_t)w;
+  return out;
+}
+
+/* container -> header fields; offs (int64[2^N + 1]) and keys (caller-sized by a first call
+ * with offs == NULL, which only fills the header outputs). Returns 0, -1 on corruption. */
+int kmsc_o_codec_decode(const uint8_t* bytes, int64_t n_bytes, int* K, int* N, int* key_bytes, int64_t* n_keys,
+                        int64_t* offs, void* keys) {
+  if (n_bytes < 48) return -1;
+  uint32_t h32[6]; uint64_t h64[3];
+  memcpy(h32, bytes, 24); memcpy(h64, bytes + 24, 24);
+  if (h32[0] != 0x43534D4Bu || h32[1] != 1u) return -1;
+  *K = (int)h32[2]; *N = (int)h32[3]; *key_bytes = (int)h32[4]; *n_keys = (int64_t)h64[0];
+  if (!offs) return 0;
+  const uint64_t nb = (uint64_t)1 << *N;
+  const int wpk = (int)h32[5];
+  const uint64_t n = h64[0], m = n * (uint64_t)wpk;
+  const size_t n_sctrl = (size_t)(nb + 3) / 4, n_kctrl = (size_t)(m + 3) / 4;
+  if ((uint64_t)n_bytes != 48 + n_sctrl + h64[1] + n_kctrl + h64[2]) return -1;
+  uint32_t* sv = (uint32_t*)malloc((size_t)(nb + 1) * 4);
+  uint32_t* kv = (uint32_t*)malloc((size_t)(m + 1) * 4);
+  const uint8_t* p = bytes + 48;
+  int rc = codec_stream_decode(p, p + n_sctrl, (size_t)h64[1], nb, sv);
+  p += n_sctrl + h64[1];
+  if (rc == 0) rc = codec_stream_decode(p, p + n_kctrl, (size_t)h64[2], m, kv);
+  if (rc == 0) {
+    offs[0] = 0;
+    for (uint64_t b = 0; b < nb; b++) offs[b + 1] = offs[b] + sv[b];
+    if ((uint64_t)offs[nb] != n) rc = -1;
+  }
+  if (rc == 0) {
+    for (uint64_t b = 0; b < nb; b++) {
+      uint64_t prev = 0;
+      for (int64_t i = offs[b]; i < offs[b + 1]; i++) {
+        uint64_t d = kv[(uint64_t)i * wpk];
+        if (wpk == 2) d |= (uint64_t)kv[(uint64_t)i * wpk + 1] << 32;
+        prev += d;
+        if (*key_bytes == 2) ((uint16_t*)keys)[i] = (uint16_t)prev;
+        else if (*key_bytes == 4) ((uint32_t*)keys)[i] = (uint32_t)prev;
+        else ((uint64_t*)keys)[i] = prev;
+      }
+    }
+  }
+  free(sv); free(kv);
+  return rc;
+}
+
 void kmsc_o_free(void* p) { free(p); }
 
 /* ------------------------------------------------------------------------- */

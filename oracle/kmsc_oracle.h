@@ -133,6 +133,11 @@ size_t   kmsc_o_svb0124_max_bytes(uint32_t n);
 size_t   kmsc_o_svb0124_encode(const uint32_t* in, uint32_t n, uint8_t* out);
 size_t   kmsc_o_svb0124_decode(const uint8_t* in, uint32_t* out, uint32_t n);
 
+/* ---- P6: "KMSC" container (delta + 1/2/3/4-byte codes); no reference counterpart ---- */
+uint8_t* kmsc_o_codec_encode(int K, int N, int key_bytes, const int64_t* offs, const void* keys, int64_t* n_bytes);
+int      kmsc_o_codec_decode(const uint8_t* bytes, int64_t n_bytes, int* K, int* N, int* key_bytes, int64_t* n_keys,
+                             int64_t* offs, void* keys);
+
 void     kmsc_o_free(void* p);
 
 #ifdef __cplusplus

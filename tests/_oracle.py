@@ -115,6 +115,11 @@ class Oracle:
         L.kmsc_o_svb0124_encode.restype = C.c_size_t
         L.kmsc_o_svb0124_decode.argtypes = [u8p, u32p, C.c_uint32]
         L.kmsc_o_svb0124_decode.restype = C.c_size_t
+        L.kmsc_o_codec_encode.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64)]
+        L.kmsc_o_codec_encode.restype = C.c_void_p
+        L.kmsc_o_codec_decode.argtypes = [u8p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
+        L.kmsc_o_codec_decode.restype = C.c_int
         L.kmsc_o_free.argtypes = [C.c_void_p]
 
     # -- Kmer ---------------------------------------------------------------
@@ -285,6 +290,31 @@ class Oracle:
         out = np.zeros(self.lib.kmsc_o_svb0124_max_bytes(len(vals)) + 8, np.uint8)
         n = self.lib.kmsc_o_svb0124_encode(_ptr(vals, u32p), len(vals), _ptr(out, u8p))
         return out[:n].copy()
+
+    # P6 container (no reference counterpart; layout in csrc/codec.cu)
+    def codec_encode(self, K, N, key_bytes, offs, keys) -> bytes:
+        offs = np.ascontiguousarray(offs, np.int64)
+        keys = np.ascontiguousarray(keys, {2: np.uint16, 4: np.uint32, 8: np.uint64}[key_bytes])
+        n = C.c_int64()
+        p = self.lib.kmsc_o_codec_encode(K, N, key_bytes, offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                         keys.ctypes.data if len(keys) else None, C.byref(n))
+        data = C.string_at(p, n.value)
+        self.lib.kmsc_o_free(p)
+        return data
+
+    def codec_decode(self, data: bytes):
+        buf = np.frombuffer(data, np.uint8)
+        K, N, kb, nk = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        rc = self.lib.kmsc_o_codec_decode(_ptr(buf, u8p), len(buf), C.byref(K), C.byref(N), C.byref(kb), C.byref(nk), None, None)
+        if rc != 0:
+            raise ValueError("corrupt container")
+        offs = np.zeros((1 << N.value) + 1, np.int64)
+        keys = np.zeros(max(1, nk.value), {2: np.uint16, 4: np.uint32, 8: np.uint64}[kb.value])
+        rc = self.lib.kmsc_o_codec_decode(_ptr(buf, u8p), len(buf), C.byref(K), C.byref(N), C.byref(kb), C.byref(nk),
+                                          offs.ctypes.data_as(C.POINTER(C.c_int64)), keys.ctypes.data)
+        if rc != 0:
+            raise ValueError("corrupt container")
+        return K.value, N.value, kb.value, offs, keys[:nk.value]
 
     def svb_decode(self, data, n):
         data = np.ascontiguousarray(data, np.uint8)
