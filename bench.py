@@ -51,8 +51,8 @@ UNIT = "key-visits/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sets", type=int, default=64)
     ap.add_argument("--kmers", type=int, default=10_000_000, help="k-mers per set per GPU")
@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--ref-sets", type=int, default=0, help="sets in the reference sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stage", action="store_true")
     return ap.parse_args()
 
 
@@ -94,45 +95,54 @@ def pack_torch(codes):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every
+    few milliseconds (the timed region of a short run lasts tens of milliseconds)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.mx, self.reasons = [], None, set()
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            dev = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(dev.split(",")[gpu_index]) if dev and dev.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _poll(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self._h is not None:
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) > 8:
-                for nme, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ----------------------------------------------------------------------------
@@ -321,6 +331,42 @@ def main():
     value = visits_total * args.steps / (ms / 1e3)
     W = d_out.cpu().numpy().reshape(n, n)
 
+    # ---- "pairwise-weight plus diff" stage: the matrix + one split per spanning-tree edge ----
+    # (north_star: MST over d(i,j) = |Si| + |Sj| - 2 W[i][j]; per edge the two difference sets
+    # via kmsc_pair_split). Bytes are the algorithmic B_w + sum B_s of SURVEY 8(d).
+    stage = None
+    if not args.no_stage:
+        sizes = np.diag(W).astype(np.int64)
+        dist_m = sizes[:, None] + sizes[None, :] - 2 * W
+        in_tree, parent, best = np.zeros(n, bool), np.zeros(n, np.int64), np.full(n, np.iinfo(np.int64).max)
+        in_tree[0] = True
+        best[1:], parent[1:] = dist_m[0, 1:], 0
+        edges = []
+        for _ in range(n - 1):  # Prim; ties -> smallest index
+            cand = np.where(in_tree, np.iinfo(np.int64).max, best)
+            c = int(np.argmin(cand))
+            edges.append((int(parent[c]), c))
+            in_tree[c] = True
+            upd = (~in_tree) & (dist_m[c] < best)
+            best[upd], parent[upd] = dist_m[c][upd], c
+        barrier()
+        split_bytes = 0
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record(stream)
+        for (pa, ch) in edges:
+            _, only_p, only_c = ctx.pair_split(sets[pa], sets[ch], want_inter=False)
+            split_bytes += (sets[pa].n_keys + sets[ch].n_keys + only_p.n_keys + only_c.n_keys) * KB + 5 * ((1 << N) + 1) * 4
+            only_p.free(); only_c.free()
+        es1.record(stream)
+        barrier()
+        split_ms = es0.elapsed_time(es1)
+        w_ms = ms / args.steps
+        w_bytes = algo_bytes / max(1, main_launches)
+        stage = {"what": "all-pairs matrix + the two difference sets of each of the n-1 MST edges, per GPU",
+                 "ms": w_ms + split_ms, "weights_ms": w_ms, "splits_ms": split_ms, "n_splits": len(edges),
+                 "algorithmic_bytes": w_bytes + split_bytes,
+                 "achieved_gbs": (w_bytes + split_bytes) / ((w_ms + split_ms) / 1e3) / 1e9}
+
     # ---- e2e: host packed SPSS -> device CSR -> matrix -> host ------------------------
     e2e = None
     if not args.no_e2e:
@@ -374,6 +420,8 @@ def main():
                 "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": main_ms / ms if ms else None,
                 "plan_ms_per_step": plan_ms / args.steps}
 
+    if stage is not None:
+        stage["frac_of_hbm_peak"] = stage["achieved_gbs"] / peak
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from _oracle import Ref
@@ -394,7 +442,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage": stage, "cpu_baseline": cpu_baseline,
             "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local)}}
     print(json.dumps(line))
     if world > 1:

@@ -46,7 +46,6 @@ void Scratch::release() {
 int ctx_pinned(kmsc_ctx* ctx, size_t bytes, void** out) {
   if (bytes > ctx->pinned_cap) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  for (int i = 0; i < 3; i++) if (ctx->pc_ev[i]) cudaEventDestroy(ctx->pc_ev[i]);
     ctx->pinned = nullptr;
     ctx->pinned_cap = 0;
     size_t want = bytes + bytes / 4 + 4096;
@@ -313,6 +312,8 @@ void kmsc_ctx_destroy(kmsc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->plan.release(); ctx->work.release(); ctx->work2.release(); ctx->work3.release(); ctx->stage.release(); ctx->small.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < 3; i++)
+    if (ctx->pc_ev[i]) cudaEventDestroy(ctx->pc_ev[i]);
   if (ctx->last_counted_owned && ctx->last_counted) { kmsc_set* lc = ctx->last_counted; ctx->last_counted = nullptr; kmsc_set_free(ctx, lc); }
   if (ctx->last_counts) cudaFree(ctx->last_counts);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

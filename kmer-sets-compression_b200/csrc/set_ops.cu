@@ -113,24 +113,31 @@ static int merge_count(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, Merg
   mp->NF = (uint32_t)1 << (a->N + mp->F);
   const size_t ent = (size_t)mp->NF + 1;
   const size_t sb = scan_scratch_entries(mp->NF);
-  KMSC_TRY(ctx->work2.reserve((ent * 4 + sb + 16) * 4));
+  KMSC_TRY(ctx->work2.reserve((ent * 4 + sb * 4 + 16) * 4));
   uint32_t* p = (uint32_t*)ctx->work2.p;
   mp->cI = p; p += ent;
   mp->cA = p; p += ent;
   mp->cB = p; p += ent;
   mp->cU = p; p += ent;
-  mp->bsum = p; p += sb;
+  mp->bsum = p; p += sb * 4;
   mp->totals = p;
   dispatch_classify(ctx, false, a, b, *mp, nullptr, nullptr, nullptr, nullptr);
   KMSC_CUDA(cudaGetLastError());
+  ScanMulti sm{};
+  uint32_t* arr[4] = {mp->cI, mp->cA, mp->cB, mp->cU};
+  int cnt = 3;
   if (want_union) {
     add3_kernel<<<(mp->NF + 255) / 256, 256, 0, ctx->stream>>>(mp->cI, mp->cA, mp->cB, mp->cU, mp->NF);
     count_launch(ctx);
-    KMSC_TRY(exclusive_scan_u32(ctx, mp->cU, mp->cU, mp->NF, mp->bsum, mp->totals + 3));
+    cnt = 4;
   }
-  KMSC_TRY(exclusive_scan_u32(ctx, mp->cI, mp->cI, mp->NF, mp->bsum, mp->totals + 0));
-  KMSC_TRY(exclusive_scan_u32(ctx, mp->cA, mp->cA, mp->NF, mp->bsum, mp->totals + 1));
-  KMSC_TRY(exclusive_scan_u32(ctx, mp->cB, mp->cB, mp->NF, mp->bsum, mp->totals + 2));
+  const size_t sbe = scan_scratch_entries(mp->NF);
+  for (int q = 0; q < cnt; q++) {
+    sm.in[q] = arr[q]; sm.out[q] = arr[q];
+    sm.bsum[q] = mp->bsum + (size_t)q * sbe;
+    sm.total[q] = mp->totals + q;
+  }
+  KMSC_TRY(exclusive_scan_multi_u32(ctx, sm, cnt, mp->NF));
   void* pin = nullptr;
   KMSC_TRY(ctx_pinned(ctx, 64, &pin));
   KMSC_CUDA(cudaMemcpyAsync(pin, mp->totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -139,17 +146,47 @@ static int merge_count(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, Merg
   return KMSC_OK;
 }
 
-// new set whose finest-level offsets are d_offs (NF + 1 entries)
-static int set_from_fine_offsets(kmsc_ctx* ctx, const kmsc_set* like, int64_t n_keys, const uint32_t* d_offs,
-                                 uint32_t NF, kmsc_set** out) {
-  kmsc_set* s = nullptr;
-  KMSC_TRY(set_alloc(ctx, like->K, like->N, like->key_bytes, n_keys, &s));
-  cudaError_t e = cudaMemcpyAsync(s->lev[s->max_level], d_offs, ((size_t)NF + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream);
-  if (e != cudaSuccess) { kmsc_set_free(ctx, s); return cuda_fail(e, "copy offsets", __FILE__, __LINE__); }
-  int rc = set_derive_levels(ctx, s);
-  if (rc != KMSC_OK) { kmsc_set_free(ctx, s); return rc; }
-  s->has_dups = 0;
-  *out = s;
+// all offset levels of up to three new sets from their finest-level offsets (NF + 1 entries
+// each): lev[f][x >> (F - f)] = fine[x] wherever x is a multiple of 2^(F - f)
+struct LevFill {
+  const uint32_t* src[3];
+  uint32_t* lev_base[3];
+};
+__global__ void fill_levels_kernel(LevFill lf, int N, int F, uint32_t NF) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x > NF) return;
+  const uint32_t v = lf.src[blockIdx.y][x];
+  uint32_t* base = lf.lev_base[blockIdx.y];
+  for (int f = F; f >= 0; f--) {
+    const int sh = F - f;
+    if (x & ((1u << sh) - 1u)) break;
+    const size_t start = ((size_t)1 << N) * (((size_t)1 << f) - 1) + (size_t)f;  // levels 0..f-1 hold 2^(N+g) + 1 entries
+    base[start + (x >> sh)] = v;
+  }
+}
+
+// new sets (same K, N, KeyType as `like`) with n_keys[q] keys whose finest offsets are d_offs[q]
+static int sets_from_fine_offsets(kmsc_ctx* ctx, const kmsc_set* like, int count, const int64_t* n_keys,
+                                  uint32_t* const* d_offs, uint32_t NF, kmsc_set** out) {
+  LevFill lf{};
+  for (int q = 0; q < count; q++) out[q] = nullptr;
+  for (int q = 0; q < count; q++) {
+    int rc = set_alloc(ctx, like->K, like->N, like->key_bytes, n_keys[q], &out[q]);
+    if (rc != KMSC_OK) {
+      for (int r = 0; r < q; r++) { kmsc_set_free(ctx, out[r]); out[r] = nullptr; }
+      return rc;
+    }
+    out[q]->has_dups = 0;
+    lf.src[q] = d_offs[q];
+    lf.lev_base[q] = out[q]->lev_base;
+  }
+  fill_levels_kernel<<<dim3((NF + 1 + 255) / 256, count), 256, 0, ctx->stream>>>(lf, like->N, like->max_level, NF);
+  count_launch(ctx);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    for (int q = 0; q < count; q++) { kmsc_set_free(ctx, out[q]); out[q] = nullptr; }
+    return cuda_fail(e, "fill levels", __FILE__, __LINE__);
+  }
   return KMSC_OK;
 }
 
@@ -169,9 +206,17 @@ int kmsc_pair_split(kmsc_ctx* ctx, const kmsc_set* j, const kmsc_set* k, kmsc_se
   KMSC_TRY(merge_count(ctx, j, k, &mp, false, tot));
   kmsc_set *sI = nullptr, *sA = nullptr, *sB = nullptr;
   int rc = KMSC_OK;
-  if (inter) rc = set_from_fine_offsets(ctx, j, tot[0], mp.cI, mp.NF, &sI);
-  if (rc == KMSC_OK && j_minus) rc = set_from_fine_offsets(ctx, j, tot[1], mp.cA, mp.NF, &sA);
-  if (rc == KMSC_OK && k_minus) rc = set_from_fine_offsets(ctx, j, tot[2], mp.cB, mp.NF, &sB);
+  {
+    int64_t nk[3]; uint32_t* src[3]; kmsc_set* made[3]; kmsc_set** dst[3];
+    int cnt = 0;
+    if (inter) { nk[cnt] = tot[0]; src[cnt] = mp.cI; dst[cnt++] = &sI; }
+    if (j_minus) { nk[cnt] = tot[1]; src[cnt] = mp.cA; dst[cnt++] = &sA; }
+    if (k_minus) { nk[cnt] = tot[2]; src[cnt] = mp.cB; dst[cnt++] = &sB; }
+    if (cnt > 0) {
+      rc = sets_from_fine_offsets(ctx, j, cnt, nk, src, mp.NF, made);
+      if (rc == KMSC_OK) for (int q = 0; q < cnt; q++) *dst[q] = made[q];
+    }
+  }
   if (rc == KMSC_OK) {
     dispatch_classify(ctx, true, j, k, mp, sI ? sI->keys : nullptr, sA ? sA->keys : nullptr,
                       sB ? sB->keys : nullptr, nullptr);
@@ -217,7 +262,8 @@ int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_s
     kmsc_set* u = nullptr;
     if (rc == KMSC_OK) {
       const int64_t nu = (m == 1) ? a->n_keys : (int64_t)tot[0] + tot[1] + tot[2];
-      rc = set_from_fine_offsets(ctx, a, nu, mp.cU, mp.NF, &u);
+      uint32_t* src[1] = {mp.cU};
+      rc = sets_from_fine_offsets(ctx, a, 1, &nu, src, mp.NF, &u);
     }
     if (rc == KMSC_OK) {
       dispatch_classify(ctx, true, a, b, mp, nullptr, nullptr, nullptr, u->keys);

@@ -266,10 +266,10 @@ class Context:
         return out
 
     # -- P4 -------------------------------------------------------------------------
-    def pair_split(self, j: DeviceSet, k: DeviceSet):
+    def pair_split(self, j: DeviceSet, k: DeviceSet, want_inter: bool = True):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _check(lib().kmsc_pair_split(self.h, j.h, k.h, C.byref(a), C.byref(b), C.byref(c)))
-        return DeviceSet(self, a.value), DeviceSet(self, b.value), DeviceSet(self, c.value)
+        _check(lib().kmsc_pair_split(self.h, j.h, k.h, C.byref(a) if want_inter else None, C.byref(b), C.byref(c)))
+        return (DeviceSet(self, a.value) if want_inter else None), DeviceSet(self, b.value), DeviceSet(self, c.value)
 
     def set_union(self, sets) -> DeviceSet:
         h = C.c_void_p()
