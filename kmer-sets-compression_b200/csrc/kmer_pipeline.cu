@@ -62,26 +62,51 @@ __global__ void scatter_kernel(KP kp, const uint32_t* __restrict__ offs, uint32_
   }
 }
 
-// thread per fine bucket: short runs are rank-sorted tmp -> out, long ones queued
+// thread per fine bucket: short runs are rank-sorted tmp -> out, long ones queued. Runs of up
+// to 16 keys (the common case: ~10 keys per finest bucket) are sorted out of registers: one
+// load per key instead of one per comparison. dup_flag is raised when a run holds equal keys.
 template <typename KeyT>
 __global__ void sort_runs_kernel(const KeyT* __restrict__ tmp, const uint32_t* __restrict__ offs, uint32_t NF,
                                  KeyT* __restrict__ out, uint32_t* __restrict__ big_list,
-                                 uint32_t* __restrict__ big_count) {
+                                 uint32_t* __restrict__ big_count, uint32_t* __restrict__ dup_flag) {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= NF) return;
   const uint32_t a = offs[x], b = offs[x + 1], L = b - a;
   if (L == 0) return;
   if (L == 1) { out[a] = tmp[a]; return; }
   if (L > kRankSortMax) { big_list[atomicAdd(big_count, 1u)] = x; return; }
-  for (uint32_t i = a; i < b; i++) {
-    const KeyT ki = tmp[i];
-    uint32_t r = 0;
-    for (uint32_t j = a; j < b; j++) {
-      const KeyT kj = tmp[j];
-      r += (kj < ki) || (kj == ki && j < i);
+  bool dup = false;
+  if (L <= 16) {
+    KeyT k[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) k[i] = (uint32_t)i < L ? tmp[a + i] : (KeyT)0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if ((uint32_t)i < L) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          if ((uint32_t)j < L) {
+            r += (k[j] < k[i]) || (k[j] == k[i] && j < i);
+            dup |= (j < i) && (k[j] == k[i]);
+          }
+        }
+        out[a + r] = k[i];
+      }
     }
-    out[a + r] = ki;
+  } else {
+    for (uint32_t i = a; i < b; i++) {
+      const KeyT ki = tmp[i];
+      uint32_t r = 0;
+      for (uint32_t j = a; j < b; j++) {
+        const KeyT kj = tmp[j];
+        r += (kj < ki) || (kj == ki && j < i);
+        dup |= (kj == ki) && (j < i);
+      }
+      out[a + r] = ki;
+    }
   }
+  if (dup) *dup_flag = 1u;
 }
 
 // CTA per queued long run: bitonic sort in shared memory (L <= kSmemSortMax);
@@ -90,7 +115,7 @@ template <typename KeyT>
 __global__ void sort_big_kernel(const KeyT* __restrict__ tmp, const uint32_t* __restrict__ offs,
                                 KeyT* __restrict__ out, const uint32_t* __restrict__ big_list,
                                 const uint32_t* __restrict__ big_count, uint32_t* __restrict__ huge_list,
-                                uint32_t* __restrict__ huge_count) {
+                                uint32_t* __restrict__ huge_count, uint32_t* __restrict__ dup_flag) {
   __shared__ KeyT sk[kSmemSortMax];
   const uint32_t nbig = *big_count;
   for (uint32_t t = blockIdx.x; t < nbig; t += gridDim.x) {
@@ -119,7 +144,10 @@ __global__ void sort_big_kernel(const KeyT* __restrict__ tmp, const uint32_t* __
       }
     }
     // INF padding sorts last; real keys equal to INF are still among the first L
-    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) out[a + i] = sk[i];
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+      out[a + i] = sk[i];
+      if (i + 1 < L && sk[i] == sk[i + 1]) *dup_flag = 1u;
+    }
     __syncthreads();
   }
 }
@@ -235,12 +263,14 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
   const int64_t n_occ = *(uint32_t*)pin;
   res->n_occurrences = n_occ;
 
-  kmsc_set* s_all = nullptr;      // mode 0 result
+  kmsc_set* s_all = nullptr;      // mode 0 result; mode 1 result too when no key repeats
   KeyT* d_tmp = nullptr;
   KeyT* d_sorted = nullptr;
   KMSC_TRY(ctx->work2.reserve((size_t)(n_occ + 8) * sizeof(KeyT)));
   d_tmp = (KeyT*)ctx->work2.p;
-  if (opt.mode == 0) {
+  // dedup (mode 1) sorts straight into the result set: an SPSS spells every k-mer once, so the
+  // sorted occurrences normally ARE the set and the run-length pass is skipped
+  if (opt.mode == 0 || opt.mode == 1) {
     KMSC_TRY(set_alloc(ctx, opt.K, opt.N, opt.key_bytes, n_occ, &s_all));
     d_sorted = (KeyT*)s_all->keys;
   } else {
@@ -249,20 +279,23 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
     d_sorted = (KeyT*)ctx->work3.p;
   }
   auto fail = [&](int rc) { if (s_all) kmsc_set_free(ctx, s_all); return rc; };
+  bool has_repeats = false, repeats_known = true;
 
   if (n_occ > 0) {
     scatter_kernel<KeyT><<<pos_blocks, threads, 0, ctx->stream>>>(kp, d_offs, d_aux, d_tmp);
-    sort_runs_kernel<KeyT><<<(NF + 127) / 128, 128, 0, ctx->stream>>>(d_tmp, d_offs, NF, d_sorted, d_big, d_ctr + 1);
+    sort_runs_kernel<KeyT><<<(NF + 127) / 128, 128, 0, ctx->stream>>>(d_tmp, d_offs, NF, d_sorted, d_big, d_ctr + 1, d_ctr + 3);
     sort_big_kernel<KeyT><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_tmp, d_offs, d_sorted, d_big, d_ctr + 1,
-                                                                     d_huge, d_ctr + 2);
+                                                                     d_huge, d_ctr + 2, d_ctr + 3);
     count_launch(ctx, 3);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline sort", __FILE__, __LINE__));
     // huge runs (> kSmemSortMax keys in one fine bucket): host-driven global bitonic sort
-    e = cudaMemcpyAsync(pin, d_ctr + 2, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaMemcpyAsync(pin, d_ctr + 2, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline huge count", __FILE__, __LINE__));
-    const uint32_t n_huge = *(uint32_t*)pin;
+    const uint32_t n_huge = ((uint32_t*)pin)[0];
+    has_repeats = ((uint32_t*)pin)[1] != 0 || n_huge > 0;  // huge runs are not checked: assume repeats
+    repeats_known = n_huge == 0;
     if (n_huge > 0) {
       std::vector<uint32_t> huge(n_huge);
       e = cudaMemcpy(huge.data(), d_huge, (size_t)n_huge * 4, cudaMemcpyDeviceToHost);
@@ -290,16 +323,16 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
     }
   }
 
-  if (opt.mode == 0) {
+  if (opt.mode == 0 || (opt.mode == 1 && !has_repeats)) {
     cudaError_t e = cudaMemcpyAsync(s_all->lev[s_all->max_level], d_offs, ent * 4, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline offsets", __FILE__, __LINE__));
     int rc = set_derive_levels(ctx, s_all);
     if (rc != KMSC_OK) return fail(rc);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline finish", __FILE__, __LINE__));
-    s_all->has_dups = -1;
+    s_all->has_dups = opt.mode == 1 ? 0 : (!repeats_known ? -1 : has_repeats ? 1 : 0);
     res->set = s_all;
-    res->n_distinct = -1;
+    res->n_distinct = opt.mode == 1 ? n_occ : -1;
     return KMSC_OK;
   }
 
@@ -319,7 +352,10 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
   res->n_distinct = (int64_t)nd;
 
   kmsc_set* s = nullptr;
-  KMSC_TRY(set_alloc(ctx, opt.K, opt.N, opt.key_bytes, n_kept, &s));
+  {
+    int rc_alloc = set_alloc(ctx, opt.K, opt.N, opt.key_bytes, n_kept, &s);
+    if (rc_alloc != KMSC_OK) return fail(rc_alloc);
+  }
   uint8_t* d_counts = nullptr;
   if (opt.mode == 2) {
     cudaError_t e = cudaMalloc(&d_counts, (size_t)n_kept + 16);
@@ -334,6 +370,7 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "pipeline finish", __FILE__, __LINE__);
   }
+  if (s_all) { kmsc_set_free(ctx, s_all); s_all = nullptr; }  // mode 1 with repeats: it was the sort buffer
   if (rc != KMSC_OK) { kmsc_set_free(ctx, s); if (d_counts) cudaFree(d_counts); return rc; }
   s->has_dups = 0;
   res->set = s;
