@@ -160,6 +160,19 @@ int kmsc_count_get(kmsc_ctx* ctx, uint64_t kmer, int* count);
  * ALL distinct k-mers (the set a cutoff <= 1 call returns); out holds n entries. */
 int kmsc_count_last_counts(kmsc_ctx* ctx, uint8_t* out, int64_t n);
 
+/* Streaming form for inputs that do not fit one call (config 4: a 20 GB read file): the host
+ * feeds chunks made of WHOLE records (FASTA: an even number of lines; reads: whole lines),
+ * each chunk is counted on the device and merged into the counter with saturating uint8
+ * adds (lib/core/kmer_counter.h:28-38, 105-126); finish applies ToKmerSet(cutoff) (:213-243)
+ * and leaves the counter in the context for kmsc_count_get / kmsc_count_last_counts. */
+typedef struct kmsc_counter kmsc_counter;
+int kmsc_counter_create(kmsc_ctx* ctx, int K, int N, int key_bytes, int canonical, kmsc_counter** out);
+int kmsc_counter_add_fasta(kmsc_ctx* ctx, kmsc_counter* c, const char* fasta, int64_t n_bytes);
+int kmsc_counter_add_reads(kmsc_ctx* ctx, kmsc_counter* c, const char* reads, int64_t n_bytes);
+int kmsc_counter_finish(kmsc_ctx* ctx, kmsc_counter* c, int cutoff, kmsc_set** out, int64_t* cutoff_count,
+                        int64_t* n_distinct);
+void kmsc_counter_free(kmsc_ctx* ctx, kmsc_counter* c);
+
 /* ---- P5: dense-bitmap Gram for K <= 15 ---------------------------------------------- */
 /* out[i*n + j] = |S_i & S_j| over 2^(2K)-bit bitmaps (exact all-bucket matrix);
  * same result as kmsc_pair_counts(bucket_ids = NULL) for duplicate-free sets. */

@@ -294,4 +294,93 @@ int kmsc_count_last_counts(kmsc_ctx* ctx, uint8_t* out, int64_t n) {
   return KMSC_OK;
 }
 
+/* ---- streaming counter: chunks of a FASTA / read file are counted one at a time ----------- */
+
+struct kmsc_counter {
+  int K, N, key_bytes, canonical;
+  kmsc_set* acc;        // all distinct k-mers so far
+  uint8_t* counts;      // device, aligned with acc's keys
+};
+
+int kmsc_counter_create(kmsc_ctx* ctx, int K, int N, int key_bytes, int canonical, kmsc_counter** out) {
+  if (!ctx || !out) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  if (K < 1 || K > 32 || N < 0 || N > 2 * K || 2 * K - N > 8 * key_bytes || (key_bytes != 2 && key_bytes != 4 && key_bytes != 8)) {
+    set_error("bad K/N/key_bytes");
+    return KMSC_E_INVALID;
+  }
+  kmsc_counter* c = new kmsc_counter();
+  c->K = K; c->N = N; c->key_bytes = key_bytes; c->canonical = canonical ? 1 : 0;
+  c->acc = nullptr; c->counts = nullptr;
+  *out = c;
+  return KMSC_OK;
+}
+
+static int counter_add(kmsc_ctx* ctx, kmsc_counter* c, const char* text, int64_t n, int fasta) {
+  if (!ctx || !c) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  kmsc_set* s = nullptr;
+  int64_t cut = 0, nd = 0;
+  KMSC_TRY(count_common(ctx, c->K, c->N, c->key_bytes, text, n, c->canonical, /*cutoff=*/1, fasta, &s, &cut, &nd));
+  // count_common left the chunk's counter in the context (borrowed set + owned counts): take both
+  uint8_t* sc = ctx->last_counts;
+  ctx->last_counts = nullptr; ctx->last_counted = nullptr; ctx->last_counted_owned = false;
+  if (!c->acc) { c->acc = s; c->counts = sc; return KMSC_OK; }
+  kmsc_set* u = nullptr;
+  uint8_t* uc = nullptr;
+  const int rc = counted_union(ctx, c->acc, c->counts, s, sc, &u, &uc);
+  kmsc_set_free(ctx, s);
+  if (sc) cudaFree(sc);
+  if (rc != KMSC_OK) return rc;
+  kmsc_set_free(ctx, c->acc);
+  if (c->counts) cudaFree(c->counts);
+  c->acc = u; c->counts = uc;
+  return KMSC_OK;
+}
+
+int kmsc_counter_add_fasta(kmsc_ctx* ctx, kmsc_counter* c, const char* fasta, int64_t n_bytes) {
+  return counter_add(ctx, c, fasta, n_bytes, 1);
+}
+int kmsc_counter_add_reads(kmsc_ctx* ctx, kmsc_counter* c, const char* reads, int64_t n_bytes) {
+  return counter_add(ctx, c, reads, n_bytes, 0);
+}
+
+int kmsc_counter_finish(kmsc_ctx* ctx, kmsc_counter* c, int cutoff, kmsc_set** out, int64_t* cutoff_count,
+                        int64_t* n_distinct) {
+  if (!ctx || !c || !out) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  if (!c->acc) KMSC_TRY(counter_add(ctx, c, "", 0, 0));  // nothing added: the empty counter
+  // the accumulated counter becomes the context's counter (kmsc_count_get / kmsc_count_last_counts)
+  if (ctx->last_counted_owned && ctx->last_counted) kmsc_set_free(ctx, ctx->last_counted);
+  if (ctx->last_counts) cudaFree(ctx->last_counts);
+  ctx->last_counted = c->acc; ctx->last_counts = c->counts;
+  kmsc_set* all = c->acc;
+  c->acc = nullptr; c->counts = nullptr;
+  if (n_distinct) *n_distinct = all->n_keys;
+  const int cut8 = cutoff & 0xff;
+  if (cut8 <= 1) {
+    ctx->last_counted_owned = false;
+    *out = all;
+    if (cutoff_count) *cutoff_count = 0;
+    return KMSC_OK;
+  }
+  ctx->last_counted_owned = true;
+  kmsc_set* kept = nullptr;
+  int rc;
+  switch (all->key_bytes) {
+    case 2: rc = filter_t<uint16_t>(ctx, all, ctx->last_counts, cut8, &kept); break;
+    case 4: rc = filter_t<uint32_t>(ctx, all, ctx->last_counts, cut8, &kept); break;
+    default: rc = filter_t<unsigned long long>(ctx, all, ctx->last_counts, cut8, &kept); break;
+  }
+  if (rc != KMSC_OK) return rc;
+  *out = kept;
+  if (cutoff_count) *cutoff_count = all->n_keys - kept->n_keys;
+  return KMSC_OK;
+}
+
+void kmsc_counter_free(kmsc_ctx* ctx, kmsc_counter* c) {
+  if (!c) return;
+  if (c->acc) kmsc_set_free(ctx, c->acc);
+  if (c->counts) cudaFree(c->counts);
+  delete c;
+}
+
 }  // extern "C"

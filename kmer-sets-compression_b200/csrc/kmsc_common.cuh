@@ -92,5 +92,9 @@ int set_build_levels(kmsc_ctx* ctx, kmsc_set* s);
 // given lev[max_level] (finest) already filled, derive coarser levels by striding
 int set_derive_levels(kmsc_ctx* ctx, kmsc_set* s);
 int set_check_dups(kmsc_ctx* ctx, kmsc_set* s);
+// union of two counted sets with saturating uint8 counts (set_ops.cu); counts are device arrays
+// aligned with the keys; *out_counts is cudaMalloc'd
+int counted_union(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kmsc_set* b, const uint8_t* cb,
+                  kmsc_set** out, uint8_t** out_counts);
 
 }  // namespace kmsc

@@ -190,6 +190,86 @@ static int sets_from_fine_offsets(kmsc_ctx* ctx, const kmsc_set* like, int count
   return KMSC_OK;
 }
 
+// ---- union of two COUNTED sets (streaming KmerCounter: chunk results are merged) ------------
+// Reference semantics: KmerCounter adds with saturation at 255 (lib/core/kmer_counter.h:28-38,
+// 105-126 merges thread-local maps the same way). One thread per finest-level fine bucket.
+template <typename KeyT, bool WRITE>
+__global__ void merge_counts_kernel(const KeyT* __restrict__ ka, const uint32_t* __restrict__ la, const uint8_t* __restrict__ ca,
+                                    const KeyT* __restrict__ kb, const uint32_t* __restrict__ lb, const uint8_t* __restrict__ cb,
+                                    uint32_t NF, uint32_t* __restrict__ cU /* counts (pass 1) / offsets (pass 2) */,
+                                    KeyT* __restrict__ ok, uint8_t* __restrict__ oc) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= NF) return;
+  uint32_t i = la[x], ie = la[x + 1], j = lb[x], je = lb[x + 1];
+  uint32_t n = 0, p = WRITE ? cU[x] : 0u;
+  while (i < ie && j < je) {
+    const KeyT a = ka[i], b = kb[j];
+    if (a < b) {
+      if (WRITE) { ok[p] = a; oc[p] = ca[i]; p++; } else n++;
+      i++;
+    } else if (b < a) {
+      if (WRITE) { ok[p] = b; oc[p] = cb[j]; p++; } else n++;
+      j++;
+    } else {
+      if (WRITE) { ok[p] = a; oc[p] = (uint8_t)min(255u, (uint32_t)ca[i] + (uint32_t)cb[j]); p++; } else n++;
+      i++; j++;
+    }
+  }
+  if (WRITE) {
+    for (; i < ie; i++) { ok[p] = ka[i]; oc[p] = ca[i]; p++; }
+    for (; j < je; j++) { ok[p] = kb[j]; oc[p] = cb[j]; p++; }
+  } else {
+    cU[x] = n + (ie - i) + (je - j);
+  }
+}
+
+template <typename KeyT>
+static int counted_union_t(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kmsc_set* b, const uint8_t* cb,
+                           kmsc_set** out, uint8_t** out_counts) {
+  const int F = a->max_level;
+  const uint32_t NF = (uint32_t)1 << (a->N + F);
+  const size_t ent = (size_t)NF + 1, sb = scan_scratch_entries(NF);
+  KMSC_TRY(ctx->work2.reserve((ent + sb + 16) * 4));
+  uint32_t* cU = (uint32_t*)ctx->work2.p;
+  uint32_t* bsum = cU + ent;
+  uint32_t* total = bsum + sb;
+  const unsigned blocks = (NF + 127) / 128;
+  merge_counts_kernel<KeyT, false><<<blocks, 128, 0, ctx->stream>>>((const KeyT*)a->keys, a->lev[F], ca, (const KeyT*)b->keys,
+                                                                    b->lev[F], cb, NF, cU, nullptr, nullptr);
+  count_launch(ctx);
+  KMSC_TRY(exclusive_scan_u32(ctx, cU, cU, NF, bsum, total));
+  void* pin = nullptr;
+  KMSC_TRY(ctx_pinned(ctx, 64, &pin));
+  KMSC_CUDA(cudaMemcpyAsync(pin, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t nu = *(uint32_t*)pin;
+  kmsc_set* u = nullptr;
+  uint32_t* src[1] = {cU};
+  KMSC_TRY(sets_from_fine_offsets(ctx, a, 1, &nu, src, NF, &u));
+  uint8_t* d_counts = nullptr;
+  cudaError_t e = cudaMalloc(&d_counts, (size_t)nu + 16);
+  if (e != cudaSuccess) { kmsc_set_free(ctx, u); return cuda_fail(e, "cudaMalloc counts", __FILE__, __LINE__); }
+  merge_counts_kernel<KeyT, true><<<blocks, 128, 0, ctx->stream>>>((const KeyT*)a->keys, a->lev[F], ca, (const KeyT*)b->keys,
+                                                                   b->lev[F], cb, NF, cU, (KeyT*)u->keys, d_counts);
+  count_launch(ctx);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { kmsc_set_free(ctx, u); cudaFree(d_counts); return cuda_fail(e, "counted union", __FILE__, __LINE__); }
+  *out = u;
+  *out_counts = d_counts;
+  return KMSC_OK;
+}
+
+int counted_union(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kmsc_set* b, const uint8_t* cb,
+                  kmsc_set** out, uint8_t** out_counts) {
+  KMSC_TRY(check_pair(a, b));
+  switch (a->key_bytes) {
+    case 2: return counted_union_t<uint16_t>(ctx, a, ca, b, cb, out, out_counts);
+    case 4: return counted_union_t<uint32_t>(ctx, a, ca, b, cb, out, out_counts);
+    default: return counted_union_t<unsigned long long>(ctx, a, ca, b, cb, out, out_counts);
+  }
+}
+
 }  // namespace kmsc
 
 using namespace kmsc;

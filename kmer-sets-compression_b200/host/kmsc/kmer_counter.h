@@ -108,6 +108,35 @@ class KmerCounter {
     return std::make_pair(KmerSet<K, N, KeyType>(MakeSetPtr(s)), cut);
   }
 
+  // streaming device path for files that do not fit one call (config 4): the file is read in
+  // chunks of whole records, every chunk is counted on the GPU and merged into a device counter
+  static StatusOr<std::pair<KmerSet<K, N, KeyType>, std::int64_t>> CountFileToKmerSet(
+      const std::string& file_name, const std::string& decompressor, bool canonical, int cutoff,
+      std::size_t chunk_bytes, std::int64_t* n_distinct) {
+    kmsc_counter* c = nullptr;
+    {
+      std::lock_guard<std::mutex> l(Device::Mu());
+      Device::Check(kmsc_counter_create(Device::Ctx(), K, N, static_cast<int>(sizeof(KeyType)), canonical ? 1 : 0, &c),
+                    "kmsc_counter_create");
+    }
+    Status st = ReadRecordChunks(file_name, decompressor, chunk_bytes, [&](const char* data, std::size_t n) -> Status {
+      std::lock_guard<std::mutex> l(Device::Mu());
+      const int rc = kmsc_counter_add_fasta(Device::Ctx(), c, data, static_cast<std::int64_t>(n));
+      if (rc == KMSC_E_FORMAT) return FailedPreconditionError(kmsc_last_error());
+      if (rc != KMSC_OK) return InternalError(kmsc_last_error());
+      return OkStatus();
+    });
+    std::lock_guard<std::mutex> l(Device::Mu());
+    if (!st.ok()) { kmsc_counter_free(Device::Ctx(), c); return st; }
+    kmsc_set* s = nullptr;
+    std::int64_t cut = 0, nd = 0;
+    const int rc = kmsc_counter_finish(Device::Ctx(), c, cutoff, &s, &cut, &nd);
+    kmsc_counter_free(Device::Ctx(), c);
+    if (rc != KMSC_OK) return InternalError(kmsc_last_error());
+    if (n_distinct) *n_distinct = nd;
+    return std::make_pair(KmerSet<K, N, KeyType>(MakeSetPtr(s)), cut);
+  }
+
  private:
   Status Count(const std::string& text, bool canonical, bool fasta) {
     kmsc_set* s = nullptr;

@@ -15,10 +15,13 @@ int Main(const Flags& flags) {
   if (flags.positional.size() != 1) { Error("usage: kmerset-build [flags] <fasta>"); return 1; }
   const int n_workers = flags.Int("workers", 1);
   const bool canonical = flags.Bool("canonical", true);
-  auto text = internal::ReadAll(flags.positional[0], flags.Str("decompressor", ""));
-  if (!text.ok()) { Error("failed to read the file: " + text.status().ToString()); return 1; }
+  // the file is streamed in chunks of whole records (--chunk_mb, default 512) and counted
+  // chunk by chunk on the device; the reference holds it in memory twice (kmer_counter.h:141-157)
   std::int64_t n_distinct = 0;
-  auto counted = KmerCounter<K, N, KeyType>::CountToKmerSet(text.value(), canonical, flags.Int("cutoff", 1), &n_distinct);
+  const std::size_t chunk = flags.Int("chunk_bytes", 0) > 0 ? static_cast<std::size_t>(flags.Int("chunk_bytes", 0))
+                                                            : static_cast<std::size_t>(flags.Int("chunk_mb", 512)) << 20;
+  auto counted = KmerCounter<K, N, KeyType>::CountFileToKmerSet(flags.positional[0], flags.Str("decompressor", ""), canonical,
+                                                                flags.Int("cutoff", 1), chunk, &n_distinct);
   if (!counted.ok()) { Error("failed to parse FASTA file: " + counted.status().ToString()); return 1; }
   KmerSet<K, N, KeyType>& kmer_set = counted.value().first;
   Info("constructed kmer_counter, size = " + std::to_string(n_distinct));

@@ -32,7 +32,8 @@ EXPORTS = [
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
     "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
-    "kmsc_count_get", "kmsc_count_last_counts", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
+    "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
+    "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
 ]
 
 
@@ -96,6 +97,12 @@ def lib() -> C.CDLL:
     L.kmsc_count_reads.argtypes = L.kmsc_count_fasta.argtypes
     L.kmsc_count_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     L.kmsc_count_last_counts.argtypes = [C.c_void_p, _u8p, C.c_int64]
+    L.kmsc_counter_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.kmsc_counter_add_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
+    L.kmsc_counter_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
+    L.kmsc_counter_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _i64p, _i64p]
+    L.kmsc_counter_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.kmsc_counter_free.restype = None
     L.kmsc_bitmap_gram.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i64p]
     L.kmsc_codec_encode.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), _i64p]
     L.kmsc_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
@@ -300,6 +307,20 @@ class Context:
         v = C.c_int()
         _check(lib().kmsc_count_get(self.h, kmer, C.byref(v)))
         return v.value
+
+    def count_chunks(self, K, N, key_bytes, chunks, canonical=True, cutoff=1, fasta=True):
+        """streaming counter: every chunk holds whole records; returns (set, cutoff_count, n_distinct)"""
+        c = C.c_void_p()
+        _check(lib().kmsc_counter_create(self.h, K, N, key_bytes, int(canonical), C.byref(c)))
+        try:
+            add = lib().kmsc_counter_add_fasta if fasta else lib().kmsc_counter_add_reads
+            for ch in chunks:
+                _check(add(self.h, c, ch, len(ch)))
+            h, cut, nd = C.c_void_p(), C.c_int64(), C.c_int64()
+            _check(lib().kmsc_counter_finish(self.h, c, cutoff, C.byref(h), C.byref(cut), C.byref(nd)))
+        finally:
+            lib().kmsc_counter_free(self.h, c)
+        return DeviceSet(self, h.value), cut.value, nd.value
 
     def count_last_counts(self, n: int) -> np.ndarray:
         out = np.zeros(max(1, n), np.uint8)

@@ -100,3 +100,49 @@ def test_fasta_validation(ctx):
                 ctx.count_fasta(5, 3, 2, data, canonical=True, cutoff=1)
             want = "even number of lines" if e["rc"] == 1 else "invalid FASTA file"
             assert want in str(ei.value), (e["lines"], str(ei.value))
+
+
+@pytest.mark.parametrize("K,N", [(15, 14), (31, 14), (5, 3)])
+def test_streaming_counter_equals_one_shot(ctx, oracle, K, N):
+    """config 4 shape: the file is fed in chunks of whole records; counts are merged on the device
+    with saturating uint8 adds (kmer_counter.h:28-38, 105-126) and equal the one-shot result"""
+    rng = np.random.default_rng(K)
+    base = "".join(rng.choice(list("ACGT"), 3000))
+    reads, lines = [], []
+    for i in range(4000):
+        a = int(rng.integers(0, 2800))
+        r = base[a:a + int(rng.integers(1, 150))]
+        if rng.random() < 0.05:
+            p = int(rng.integers(0, len(r)))
+            r = r[:p] + "N" + r[p + 1:]
+        reads.append(r)
+        lines += [f">r{i}", r]
+    kmers, counts = oracle.count_reads(reads, K, True)
+    assert counts.max() == 255 or K != 5        # K = 5 saturates: exercises the 255 cap across chunks
+    cuts = [0, 1000, 1002, 3000, 7000, 8000]    # record-aligned (even) line offsets, uneven chunk sizes
+    chunks = [("\n".join(lines[a:b]) + "\n").encode() for a, b in zip(cuts, cuts[1:]) if b > a]
+    for cutoff in (1, 3):
+        kept, cut = oracle.counter_to_set(kmers, counts, cutoff)
+        s, gcut, nd = ctx.count_chunks(K, N, KB[K], chunks, canonical=True, cutoff=cutoff)
+        assert nd == len(kmers) and gcut == cut
+        assert np.array_equal(s.to_kmers(), kept)
+        one, ocut, ond = ctx.count_fasta(K, N, KB[K], b"".join(chunks), canonical=True, cutoff=cutoff)
+        assert (ocut, ond) == (gcut, nd) and np.array_equal(one.to_kmers(), s.to_kmers())
+    # the merged counter answers point queries
+    s, _, _ = ctx.count_chunks(K, N, KB[K], chunks, canonical=True, cutoff=1)
+    got = ctx.count_last_counts(s.n_keys)
+    assert np.array_equal(got, counts)
+    for i in rng.integers(0, len(kmers), 20):
+        assert ctx.count_get(int(kmers[i])) == int(counts[i])
+
+
+def test_streaming_counter_errors_and_empty(ctx):
+    import kmsc
+    s, cut, nd = ctx.count_chunks(15, 14, 2, [], canonical=True, cutoff=1)
+    assert s.Size() == 0 and nd == 0 and cut == 0
+    with pytest.raises(kmsc.KmscError) as ei:   # a chunk that ends inside a record
+        ctx.count_chunks(15, 14, 2, [b">a\nACGTACGTACGTACGTAAAA\n>b\n"], canonical=True, cutoff=1)
+    assert "even number of lines" in str(ei.value)
+    with pytest.raises(kmsc.KmscError) as ei:
+        ctx.count_chunks(15, 14, 2, [b">a\nACGT\n", b">b\nACGu\n"], canonical=True, cutoff=1)
+    assert "invalid FASTA file" in str(ei.value)

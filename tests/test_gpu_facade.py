@@ -53,7 +53,9 @@ def test_cli_end_to_end(bins, oracle, tmp_path, K):
         kept, _ = oracle.counter_to_set(kmers, counts, 2)
         want.append((len(kept), oracle.set_hash(kept)))
         out = tmp_path / f"set{i}.txt"
-        r = subprocess.run([str(bins / "kmerset-build"), f"--k={K}", "--cutoff=2", "--check", f"--out={out}", str(fasta)],
+        # K = 23 streams the file in ~20 KB chunks of whole records (the config-4 path)
+        extra = ["--chunk_bytes=20000"] if K == 23 else []
+        r = subprocess.run([str(bins / "kmerset-build"), f"--k={K}", "--cutoff=2", "--check", f"--out={out}", str(fasta)] + extra,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
         assert f"kmer_set.Size() = {len(kept)}" in r.stderr and f"kmer_set.Hash() = {oracle.set_hash(kept)}" in r.stderr
