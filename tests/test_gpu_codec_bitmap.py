@@ -35,10 +35,11 @@ def _sets(ctx, kmer_sets, K, N, kb):
     return dev, offs_l, keys_l
 
 
-@pytest.mark.parametrize("K,N,kb,n_sets", [(15, 14, 2, 8), (11, 8, 2, 70), (9, 10, 2, 5), (5, 3, 2, 3)])
+@pytest.mark.parametrize("K,N,kb,n_sets", [(15, 14, 2, 8), (11, 8, 2, 70), (9, 10, 2, 5), (5, 3, 2, 3), (9, 10, 2, 300), (11, 8, 2, 129)])
 def test_bitmap_gram_matches_merge(ctx, oracle, K, N, kb, n_sets):
     import synth
-    seqs = synth.window_sequences(n_sets, 40000, 20000, p=0.01, seed=K)
+    glen = 40000 if n_sets <= 70 else 6000   # many sets: keep the CPU oracle fast
+    seqs = synth.window_sequences(n_sets, glen, glen // 2, p=0.01, seed=K)
     sets = [synth.kmer_set_of(s, K) for s in seqs]
     sets[-1] = sets[-1][:0]  # an empty set
     dev, offs_l, keys_l = _sets(ctx, sets, K, N, kb)
@@ -48,7 +49,8 @@ def test_bitmap_gram_matches_merge(ctx, oracle, K, N, kb, n_sets):
     assert np.array_equal(got[iu], want[iu])
     assert np.array_equal(got, got.T)
     assert [int(got[i, i]) for i in range(n_sets)] == [len(s) for s in sets]
-    assert np.array_equal(got, ctx.pair_counts(dev))
+    if n_sets <= 256:  # P3 handles up to 256 sets per call
+        assert np.array_equal(got, ctx.pair_counts(dev))
     for d in dev:
         d.free()
 
