@@ -105,7 +105,8 @@ int kmsc_set_from_packed(kmsc_ctx* ctx, int K, int N, int key_bytes, const uint6
  * bucket_ids == NULL: all 2^N buckets (exact matrix); otherwise the reference's
  * sampled list (any order; an id listed twice counts once, as its map does,
  * :127-131). out is host memory (n*n int64). key_visits (may be NULL) receives
- * sum_{i<j} sum_b (len_i[b] + len_j[b]) -- the work the reference's merge does. */
+ * sum_{i<j} sum_b (len_i[b] + len_j[b]) -- the work the reference's merge does.
+ * Any n: up to 256 sets are one pass; more are covered by pairs of 128-set groups. */
 int kmsc_pair_counts(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                      const int32_t* bucket_ids, int32_t n_ids, int64_t* out, int64_t* key_visits);
 /* Same, result left in DEVICE memory d_out (n*n int64, on the context's stream):

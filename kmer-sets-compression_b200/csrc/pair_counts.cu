@@ -988,11 +988,59 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
   return KMSC_OK;
 }
 
+// W[map[a]][map[b]] = T[a][b]: places the matrix of a sub-run (m sets) into the n x n result
+__global__ void place_block_kernel(const unsigned long long* __restrict__ T, int m, const int* __restrict__ map,
+                                   unsigned long long* __restrict__ W, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * m) return;
+  const int a = t / m, b = t - a * m;
+  W[(size_t)map[a] * n + map[b]] = T[t];
+}
+
+static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                               const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W);
+
 // Core: d_W (n*n u64, device) is zeroed and filled. Synchronous at return.
+// One kernel pass holds the membership of up to 256 sets (the accumulator tile of the Gram).
+// More sets are covered by groups of 128: every pair of groups (g, h) is one 256-set run that
+// yields the blocks (g,g), (g,h), (h,g), (h,h); a block computed by several runs gets the same
+// values every time.
 int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                     const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W) {
   if (!ctx || !sets || n < 1 || !d_W) { set_error("bad argument"); return KMSC_E_INVALID; }
-  if (n > 256) { set_error("n_sets=%d > 256 not supported by this build", n); return KMSC_E_INVALID; }
+  if (n <= 256) return pair_counts_run_256(ctx, sets, n, bucket_ids, n_ids, d_W);
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  const int G = 128, n_groups = (n + G - 1) / G;
+  KMSC_TRY(ctx->work3.reserve((size_t)256 * 256 * 8 + 256 * sizeof(int)));
+  unsigned long long* d_T = (unsigned long long*)ctx->work3.p;
+  int* d_map = (int*)((unsigned char*)ctx->work3.p + (size_t)256 * 256 * 8);
+  double main_ms = 0, plan_ms = 0, algo = 0;
+  int launches = 0;
+  unsigned long long st3[3] = {0, 0, 0};
+  std::vector<const kmsc_set*> sub;
+  std::vector<int> map;
+  for (int g = 0; g < n_groups; g++)
+    for (int h = g + 1; h < n_groups; h++) {
+      sub.clear(); map.clear();
+      for (int i = g * G; i < std::min(n, (g + 1) * G); i++) { sub.push_back(sets[i]); map.push_back(i); }
+      for (int i = h * G; i < std::min(n, (h + 1) * G); i++) { sub.push_back(sets[i]); map.push_back(i); }
+      const int m = (int)sub.size();
+      KMSC_TRY(pair_counts_run_256(ctx, sub.data(), m, bucket_ids, n_ids, d_T));
+      KMSC_CUDA(cudaMemcpyAsync(d_map, map.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      place_block_kernel<<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(d_T, m, d_map, d_W, n);
+      count_launch(ctx);
+      KMSC_CUDA(cudaGetLastError());
+      KMSC_CUDA(cudaStreamSynchronize(ctx->stream));  // `map` is reused
+      main_ms += ctx->pc_main_ms; plan_ms += ctx->pc_plan_ms; algo += ctx->pc_algo_bytes; launches += ctx->pc_main_launches;
+      for (int q = 0; q < 3; q++) st3[q] += ctx->pc_last_stats[q];
+    }
+  ctx->pc_main_ms = main_ms; ctx->pc_plan_ms = plan_ms; ctx->pc_algo_bytes = algo; ctx->pc_main_launches = launches;
+  for (int q = 0; q < 3; q++) ctx->pc_last_stats[q] = st3[q];
+  return KMSC_OK;
+}
+
+static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                               const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W) {
   const kmsc_set* s0 = sets[0];
   if (!s0) { set_error("sets[0] is NULL"); return KMSC_E_INVALID; }
   int64_t total_keys = 0;

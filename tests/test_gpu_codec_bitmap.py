@@ -49,8 +49,7 @@ def test_bitmap_gram_matches_merge(ctx, oracle, K, N, kb, n_sets):
     assert np.array_equal(got[iu], want[iu])
     assert np.array_equal(got, got.T)
     assert [int(got[i, i]) for i in range(n_sets)] == [len(s) for s in sets]
-    if n_sets <= 256:  # P3 handles up to 256 sets per call
-        assert np.array_equal(got, ctx.pair_counts(dev))
+    assert np.array_equal(got, ctx.pair_counts(dev))
     for d in dev:
         d.free()
 

@@ -63,6 +63,7 @@ CASES = [  # (K, N, key_bytes, n_sets, genome_len)
     (23, 14, 4, 100, 8000),
     (23, 14, 4, 200, 5000),
     (5, 3, 2, 3, 200),
+    (23, 14, 4, 300, 3000),   # more than one 256-set accumulator tile: runs over pairs of 128-set groups
 ]
 
 
