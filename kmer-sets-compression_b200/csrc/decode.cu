@@ -122,11 +122,14 @@ static int spss_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* t
     mark_string_tails_kernel<<<(unsigned)((n_strings + 127) / 128), 128, 0, ctx->stream>>>(d_offs, n_strings, K, d_bad);
   count_launch(ctx, 2);
   KMSC_CUDA(cudaGetLastError());
-  void* pin = nullptr;
-  KMSC_TRY(ctx_pinned(ctx, 64, &pin));
-  KMSC_CUDA(cudaMemcpyAsync(pin, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (*(int*)pin) { set_error("SPSS text holds a character other than A, C, G, T"); return KMSC_E_FORMAT; }
+  if (!packed) {
+    // only ASCII input can hold a bad character (2-bit words cannot)
+    void* pin = nullptr;
+    KMSC_TRY(ctx_pinned(ctx, 64, &pin));
+    KMSC_CUDA(cudaMemcpyAsync(pin, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*(int*)pin) { set_error("SPSS text holds a character other than A, C, G, T"); return KMSC_E_FORMAT; }
+  }
 
   PipelineInput in{d_words, d_bad, n};
   PipelineOptions opt{K, N, key_bytes, canonical, bucket_lo, bucket_hi, dedup ? 1 : 0, 1};

@@ -279,7 +279,7 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
     d_sorted = (KeyT*)ctx->work3.p;
   }
   auto fail = [&](int rc) { if (s_all) kmsc_set_free(ctx, s_all); return rc; };
-  bool has_repeats = false, repeats_known = true;
+  bool has_repeats = false, repeats_known = true, levels_done = false;
 
   if (n_occ > 0) {
     scatter_kernel<KeyT><<<pos_blocks, threads, 0, ctx->stream>>>(kp, d_offs, d_aux, d_tmp);
@@ -289,7 +289,16 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
     count_launch(ctx, 3);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline sort", __FILE__, __LINE__));
-    // huge runs (> kSmemSortMax keys in one fine bucket): host-driven global bitonic sort
+    // huge runs (> kSmemSortMax keys in one fine bucket): host-driven global bitonic sort.
+    // The offset levels do not depend on the order inside a run: they are enqueued before the
+    // one synchronisation that brings back the huge-run count and the repeat flag.
+    if (s_all) {
+      e = cudaMemcpyAsync(s_all->lev[s_all->max_level], d_offs, ent * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline offsets", __FILE__, __LINE__));
+      int rc_l = set_derive_levels(ctx, s_all);
+      if (rc_l != KMSC_OK) return fail(rc_l);
+      levels_done = true;
+    }
     e = cudaMemcpyAsync(pin, d_ctr + 2, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline huge count", __FILE__, __LINE__));
@@ -324,11 +333,13 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
   }
 
   if (opt.mode == 0 || (opt.mode == 1 && !has_repeats)) {
-    cudaError_t e = cudaMemcpyAsync(s_all->lev[s_all->max_level], d_offs, ent * 4, cudaMemcpyDeviceToDevice, ctx->stream);
-    if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline offsets", __FILE__, __LINE__));
-    int rc = set_derive_levels(ctx, s_all);
-    if (rc != KMSC_OK) return fail(rc);
-    e = cudaStreamSynchronize(ctx->stream);
+    if (!levels_done) {
+      cudaError_t e = cudaMemcpyAsync(s_all->lev[s_all->max_level], d_offs, ent * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline offsets", __FILE__, __LINE__));
+      int rc = set_derive_levels(ctx, s_all);
+      if (rc != KMSC_OK) return fail(rc);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);  // immediate unless a huge run was sorted after the levels
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline finish", __FILE__, __LINE__));
     s_all->has_dups = opt.mode == 1 ? 0 : (!repeats_known ? -1 : has_repeats ? 1 : 0);
     res->set = s_all;
