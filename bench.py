@@ -373,7 +373,7 @@ def main():
         e2e_steps = max(2, min(args.steps, 5))
         host_out = np.zeros((n, n), np.int64)
 
-        def step_e2e():
+        def step_e2e_single():
             ss = build_sets()
             ctx.pair_counts_device(ss, d_out.data_ptr())
             if world > 1:
@@ -381,6 +381,55 @@ def main():
             host_out[:] = d_out.cpu().numpy().reshape(n, n)
             for s in ss:
                 s.free()
+
+        # N > 1: the decode is split over the ranks BY SET (rank r decodes sets r, r + N, ... over
+        # all buckets), one all-to-all hands every rank the slice of every set that falls into its
+        # prefix range (a bucket range of a sorted set is one contiguous key slice), and every
+        # rank imports all n sets restricted to its range. Without the exchange every rank would
+        # have to scan the whole text of every set.
+        m_own = n // world if world > 1 and n % world == 0 else 0
+        cuts_np = np.asarray(cuts, np.int32) if world > 1 else None
+
+        def step_e2e_exchange():
+            mine = [rank + j * world for j in range(m_own)]
+            full = [ctx.set_from_packed(K, N, KB, None, str_offs, words_ptr=pinned[i].data_ptr()) for i in mine]
+            ko = np.stack([ctx.set_bucket_offsets(s, cuts_np) for s in full])       # [m_own][world + 1]
+            sizes = (ko[:, 1:] - ko[:, :-1]).astype(np.int64)                        # keys of own set j for rank q
+            t_send_sz = torch.from_numpy(np.ascontiguousarray(sizes.T)).to(dev)      # [world][m_own], dest-major
+            t_recv_sz = torch.empty_like(t_send_sz)
+            dist.all_to_all_single(t_recv_sz, t_send_sz)
+            recv_sz = t_recv_sz.cpu().numpy()                                        # [src][j]
+            nbq = [int(cuts[q + 1] - cuts[q]) + 1 for q in range(world)]
+            nb_me = nbq[rank]
+            in_k = [int(sizes[:, q].sum()) for q in range(world)]
+            out_k = [int(recv_sz[r].sum()) for r in range(world)]
+            send_keys = torch.empty(max(1, sum(in_k)), dtype=torch.int32, device=dev)
+            recv_keys = torch.empty(max(1, sum(out_k)), dtype=torch.int32, device=dev)
+            send_offs = torch.empty(m_own * sum(nbq), dtype=torch.int32, device=dev)
+            recv_offs = torch.empty(world * m_own * nb_me, dtype=torch.int32, device=dev)
+            kp, op = 0, 0
+            for q in range(world):
+                for j, s in enumerate(full):
+                    ctx.set_export_range(s, int(cuts[q]), int(cuts[q + 1]), int(ko[j, q]), int(ko[j, q + 1]),
+                                         send_offs.data_ptr() + op * 4, send_keys.data_ptr() + kp * KB)
+                    kp += int(sizes[j, q]); op += nbq[q]
+            dist.all_to_all_single(recv_keys[:sum(out_k)], send_keys[:sum(in_k)], out_k, in_k)
+            dist.all_to_all_single(recv_offs, send_offs, [m_own * nb_me] * world, [m_own * x for x in nbq])
+            ss = [None] * n
+            kp = 0
+            for r in range(world):
+                for j in range(m_own):
+                    cnt = int(recv_sz[r, j])
+                    ss[r + j * world] = ctx.set_import_range(K, N, KB, lo, hi, recv_offs.data_ptr() + (r * m_own + j) * nb_me * 4,
+                                                             recv_keys.data_ptr() + kp * KB, cnt)
+                    kp += cnt
+            ctx.pair_counts_device(ss, d_out.data_ptr())
+            dist.all_reduce(d_out)
+            host_out[:] = d_out.cpu().numpy().reshape(n, n)
+            for s in ss + full:
+                s.free()
+
+        step_e2e = step_e2e_exchange if m_own > 0 else step_e2e_single
 
         for s in sets:
             s.free()
@@ -397,7 +446,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt[0])
         assert np.array_equal(host_out, W), "e2e matrix differs from the resident run"
-        e2e = {"value": visits_total * e2e_steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes_in),
+        e2e = {"value": visits_total * e2e_steps / (ms_e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(nbytes_in // world) if m_own > 0 else int(nbytes_in),
+               "how": ("decode split by set over the ranks + one all-to-all of prefix slices (NCCL) + all-reduce of the partial matrices"
+                       if m_own > 0 else "every rank decodes its prefix range of every set"),
                "d2h_bytes_per_step": int(n * n * 8), "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps}
 
     if rank != 0:

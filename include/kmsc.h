@@ -78,6 +78,23 @@ int kmsc_set_size(kmsc_ctx* ctx, const kmsc_set* set, int64_t* size);
 int kmsc_set_hash(kmsc_ctx* ctx, const kmsc_set* set, uint64_t* hash);
 int kmsc_set_info(const kmsc_set* set, int* K, int* N, int* key_bytes, int64_t* n_keys);
 
+/* ---- multi-GPU exchange: bucket ranges of a set ---------------------------------------- */
+/* A rank that decoded WHOLE sets hands every rank the part of each set inside that rank's
+ * bucket range (the sets are sorted by bucket, so a range is one contiguous key slice):
+ * the decode work is split over the ranks by set, one all-to-all moves the slices, and
+ * every rank imports all n sets restricted to its prefix range.
+ * offsets: out[i] = index of the first key of bucket buckets[i] (buckets[i] in [0, 2^N]). */
+int kmsc_set_bucket_offsets(kmsc_ctx* ctx, const kmsc_set* set, const int32_t* buckets, int32_t n, int64_t* out);
+/* device -> device on the context's stream (no synchronisation): d_offs receives
+ * bucket_hi - bucket_lo + 1 offsets rebased to 0, d_keys the keys [key_lo, key_hi) =
+ * the offsets of bucket_lo / bucket_hi from kmsc_set_bucket_offsets. */
+int kmsc_set_export_range(kmsc_ctx* ctx, const kmsc_set* set, int32_t bucket_lo, int32_t bucket_hi,
+                          int64_t key_lo, int64_t key_hi, uint32_t* d_offs, void* d_keys);
+/* the inverse: a set whose buckets outside [bucket_lo, bucket_hi) are empty; d_offs / d_keys
+ * are device memory in the layout kmsc_set_export_range writes. */
+int kmsc_set_import_range(kmsc_ctx* ctx, int K, int N, int key_bytes, int32_t bucket_lo, int32_t bucket_hi,
+                          const uint32_t* d_offs, const void* d_keys, int64_t n_keys, kmsc_set** out);
+
 /* ---- P2: SPSS text -> device set ------------------------------------------------ */
 /* Replaces KmerSetCompact::GetSampledKmerSet (lib/core/kmer_set_compact.h:120-203;
  * dedup = 0: duplicates kept) and KmerSetCompact::ToKmerSet / GetKmerSetFromSPSS

@@ -160,6 +160,23 @@ __global__ void kmers_bucket_offsets_kernel(const unsigned long long* __restrict
   offs[b] = (uint32_t)lo;
 }
 
+// ---- multi-GPU exchange helpers: bucket ranges of a set as (rebased offsets, keys) -----------
+__global__ void gather_offsets_kernel(const uint32_t* __restrict__ offs, const int32_t* __restrict__ buckets, int n,
+                                      unsigned long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = offs[buckets[i]];
+}
+__global__ void export_offsets_kernel(const uint32_t* __restrict__ offs, int lo, int n_entries, uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_entries) out[i] = offs[lo + i] - offs[lo];
+}
+__global__ void import_offsets_kernel(const uint32_t* __restrict__ in, int lo, int hi, int n_buckets, uint32_t n_keys,
+                                      uint32_t* __restrict__ offs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_buckets) return;
+  offs[b] = b <= lo ? 0u : b >= hi ? n_keys : in[b - lo];
+}
+
 static uint64_t levels_total_entries(int N, int max_level) {
   uint64_t t = 0;
   for (int f = 0; f <= max_level; f++) t += ((uint64_t)1 << (N + f)) + 1;
@@ -442,6 +459,66 @@ int kmsc_set_info(const kmsc_set* set, int* K, int* N, int* key_bytes, int64_t* 
   if (N) *N = set->N;
   if (key_bytes) *key_bytes = set->key_bytes;
   if (n_keys) *n_keys = set->n_keys;
+  return KMSC_OK;
+}
+
+int kmsc_set_bucket_offsets(kmsc_ctx* ctx, const kmsc_set* set, const int32_t* buckets, int32_t n, int64_t* out) {
+  if (!ctx || !set || !buckets || !out || n < 0) { set_error("bad argument"); return KMSC_E_INVALID; }
+  const int nb = 1 << set->N;
+  for (int i = 0; i < n; i++)
+    if (buckets[i] < 0 || buckets[i] > nb) { set_error("bucket %d out of range", buckets[i]); return KMSC_E_INVALID; }
+  if (n == 0) return KMSC_OK;
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  KMSC_TRY(ctx->small.reserve((size_t)n * 12 + 64));
+  unsigned long long* d_out = (unsigned long long*)ctx->small.p;
+  int32_t* d_b = (int32_t*)((unsigned char*)ctx->small.p + (((size_t)n * 8 + 15) & ~(size_t)15));
+  KMSC_CUDA(cudaMemcpyAsync(d_b, buckets, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  gather_offsets_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(set->lev[0], d_b, n, d_out);
+  count_launch(ctx);
+  KMSC_CUDA(cudaGetLastError());
+  KMSC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return KMSC_OK;
+}
+
+int kmsc_set_export_range(kmsc_ctx* ctx, const kmsc_set* set, int32_t bucket_lo, int32_t bucket_hi,
+                          int64_t key_lo, int64_t key_hi, uint32_t* d_offs, void* d_keys) {
+  if (!ctx || !set || !d_offs) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  const int nb = 1 << set->N;
+  if (bucket_lo < 0 || bucket_hi > nb || bucket_lo > bucket_hi || key_lo < 0 || key_hi < key_lo || key_hi > set->n_keys) {
+    set_error("bad range");
+    return KMSC_E_INVALID;
+  }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  const int n_entries = bucket_hi - bucket_lo + 1;
+  export_offsets_kernel<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(set->lev[0], bucket_lo, n_entries, d_offs);
+  count_launch(ctx);
+  KMSC_CUDA(cudaGetLastError());
+  if (key_hi > key_lo) {
+    if (!d_keys) { set_error("d_keys is NULL"); return KMSC_E_INVALID; }
+    KMSC_CUDA(cudaMemcpyAsync(d_keys, (const unsigned char*)set->keys + (size_t)key_lo * set->key_bytes,
+                              (size_t)(key_hi - key_lo) * set->key_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return KMSC_OK;
+}
+
+int kmsc_set_import_range(kmsc_ctx* ctx, int K, int N, int key_bytes, int32_t bucket_lo, int32_t bucket_hi,
+                          const uint32_t* d_offs, const void* d_keys, int64_t n_keys, kmsc_set** out) {
+  if (!ctx || !out || !d_offs || (n_keys > 0 && !d_keys)) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  if (N < 0 || N > 24 || bucket_lo < 0 || bucket_hi > (1 << N) || bucket_lo > bucket_hi) { set_error("bad range"); return KMSC_E_INVALID; }
+  kmsc_set* s = nullptr;
+  KMSC_TRY(set_alloc(ctx, K, N, key_bytes, n_keys, &s));
+  const int nb = 1 << N;
+  import_offsets_kernel<<<(nb + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_offs, bucket_lo, bucket_hi, nb, (uint32_t)n_keys, s->lev[0]);
+  count_launch(ctx);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && n_keys > 0)
+    e = cudaMemcpyAsync(s->keys, d_keys, (size_t)n_keys * key_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) { kmsc_set_free(ctx, s); return cuda_fail(e, "import range", __FILE__, __LINE__); }
+  int rc = set_build_levels(ctx, s);
+  if (rc != KMSC_OK) { kmsc_set_free(ctx, s); return rc; }
+  s->has_dups = -1;  // checked on first use by the pair counts
+  *out = s;
   return KMSC_OK;
 }
 

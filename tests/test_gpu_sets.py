@@ -162,3 +162,37 @@ def test_split_empty_and_disjoint(ctx, oracle):
     assert i.Size() == 0 and np.array_equal(x.to_kmers(), a) and y.Size() == 0
     i, x, y = ctx.pair_split(da, da)
     assert np.array_equal(i.to_kmers(), a) and x.Size() == 0 and y.Size() == 0
+
+
+def test_export_import_bucket_ranges(ctx, oracle):
+    """multi-GPU exchange helpers: a set cut into bucket ranges, every range exported to device
+    buffers and imported as a restricted set; the ranges partition the set exactly"""
+    import synth
+    import torch
+    K, N, kb = 23, 14, 4
+    km = synth.kmer_set_of(synth.random_genome(50000, K), K)
+    offs, keys = synth.csr_of(km, K, N, kb)
+    s = ctx.set_from_csr(K, N, kb, offs, keys)
+    cuts = np.array([0, 100, 100, 9000, 1 << N], np.int32)   # one empty range
+    ko = ctx.set_bucket_offsets(s, cuts)
+    assert np.array_equal(ko, offs[cuts])
+    dev = torch.device("cuda", 0)
+    parts = []
+    for q in range(len(cuts) - 1):
+        lo, hi = int(cuts[q]), int(cuts[q + 1])
+        cnt = int(ko[q + 1] - ko[q])
+        d_offs = torch.empty(hi - lo + 1, dtype=torch.int32, device=dev)
+        d_keys = torch.empty(max(1, cnt), dtype=torch.int32, device=dev)
+        ctx.set_export_range(s, lo, hi, int(ko[q]), int(ko[q + 1]), d_offs.data_ptr(), d_keys.data_ptr())
+        ctx.sync()
+        torch.cuda.synchronize()
+        p = ctx.set_import_range(K, N, kb, lo, hi, d_offs.data_ptr(), d_keys.data_ptr(), cnt)
+        po, pk = p.to_csr()
+        want_o = np.clip(offs, ko[q], ko[q + 1]) - ko[q]
+        assert np.array_equal(po, want_o) and np.array_equal(pk, keys[ko[q]:ko[q + 1]])
+        parts.append(p)
+    u = ctx.set_union(parts)
+    assert np.array_equal(u.to_kmers(), km)
+    # intersection counts add up over the ranges (what the all-reduce relies on)
+    total = sum(int(ctx.pair_counts([p, s])[0, 1]) for p in parts)
+    assert total == len(km)
