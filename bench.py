@@ -465,8 +465,17 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     per_launch_ms = main_ms / max(1, main_launches)
     achieved = (algo_bytes / max(1, main_launches)) / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch: from the committed ncu capture of this
+    # workload (it cannot be measured outside a profiler); null for any other shape
+    traffic = None
+    try:
+        tr = json.loads((ROOT / "profiles" / "p3_traffic.json").read_text())
+        if args.sets == 64 and args.kmers == 10_000_000 and K == 23:
+            traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "pair_counts_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": algo_bytes / max(1, main_launches),
                 "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": main_ms / ms if ms else None,

@@ -77,21 +77,33 @@ __global__ void sort_runs_kernel(const KeyT* __restrict__ tmp, const uint32_t* _
   if (L > kRankSortMax) { big_list[atomicAdd(big_count, 1u)] = x; return; }
   bool dup = false;
   if (L <= 16) {
+    // 16-input bitonic network in registers (80 compare-exchanges); slots past L hold the
+    // largest key value and sort to the end (a real key equal to it is still among the first L)
     KeyT k[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) k[i] = (uint32_t)i < L ? tmp[a + i] : (KeyT)0;
+    for (int i = 0; i < 16; i++) k[i] = (uint32_t)i < L ? tmp[a + i] : (KeyT)~(KeyT)0;
+#pragma unroll
+    for (int kk = 2; kk <= 16; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int l = i ^ j;
+          if (l > i) {
+            const KeyT x = k[i], y = k[l];
+            const bool up = (i & kk) == 0;
+            const KeyT lo = x < y ? x : y, hi = x < y ? y : x;
+            k[i] = up ? lo : hi;
+            k[l] = up ? hi : lo;
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       if ((uint32_t)i < L) {
-        uint32_t r = 0;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-          if ((uint32_t)j < L) {
-            r += (k[j] < k[i]) || (k[j] == k[i] && j < i);
-            dup |= (j < i) && (k[j] == k[i]);
-          }
-        }
-        out[a + r] = k[i];
+        out[a + i] = k[i];
+        if (i > 0) dup |= k[i] == k[i - 1];
       }
     }
   } else {
