@@ -114,6 +114,15 @@ int kmsc_set_from_packed(kmsc_ctx* ctx, int K, int N, int key_bytes, const uint6
                          const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
                          int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
 
+/* SPSS construction support: the de Bruijn neighbours of every k-mer of a set.
+ * out (host, 8 * n_keys int32): out[8 i + c] = Kmer::Next(base c) of k-mer i, out[8 i + 4 + c] =
+ * Kmer::Prev(base c) (lib/core/kmer.h:136-186), each -1 if absent from the set, else
+ * (index << 1) | flip, index = position in the set's key order (the order of kmsc_set_to_csr),
+ * flip = 1 if the set holds the reverse complement (canonical != 0). Replaces the hash-set
+ * Contains() calls of the reference's unitig / path-cover construction
+ * (lib/core/spss.h:230-615, 1039-1858) by one device binary search per neighbour. */
+int kmsc_set_neighbors(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int32_t* out);
+
 /* ---- P3: all-pairs intersection counts ------------------------------------------ */
 /* Replaces GetEdgeWeight and the initial all-pairs loop of KmerSetSet's
  * constructor (lib/core/kmer_set_set.h:158-219): out[i*n + j] =

@@ -52,6 +52,48 @@ __global__ void mark_string_tails_kernel(const long long* __restrict__ str_offs,
   for (long long p = a; p < e; p++) atomicOr(&bad[p >> 5], 1u << (p & 31));
 }
 
+// ---- SPSS construction support: the de Bruijn neighbours of every k-mer of a set -----------
+// out[8 i + c] (c in 0..3): the k-mer obtained by dropping the first base of k-mer i and
+// appending base c (reference Kmer::Next, lib/core/kmer.h:136-160); out[8 i + 4 + c]: dropping
+// the last base and prepending c (Kmer::Prev, :163-186). An entry is -1 if that k-mer (its
+// canonical form when `canonical`) is not in the set, else (index << 1) | flip where index is
+// its position in the set's key order and flip = 1 if the set stores its reverse complement.
+// This replaces the hash-set Contains() calls that dominate the reference's unitig / path-cover
+// construction (lib/core/spss.h:230-615, 1039-1858) by one binary search per neighbour.
+template <typename KeyT>
+__global__ void neighbors_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ offs, int n_buckets,
+                                 int K, int key_bits, int canonical, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const unsigned long long mask = K == 32 ? ~0ull : ((1ull << (2 * K)) - 1);
+  const unsigned long long kmask = key_bits == 64 ? ~0ull : ((1ull << key_bits) - 1);
+  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n_buckets; b += gridDim.x * wpb) {
+    const uint32_t lo = offs[b], hi = offs[b + 1];
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+      const unsigned long long v = ((unsigned long long)b << key_bits) | (unsigned long long)keys[i];
+#pragma unroll
+      for (int d = 0; d < 8; d++) {
+        const unsigned long long c = (unsigned long long)(d & 3);
+        unsigned long long w = d < 4 ? (((v << 2) & mask) | c) : ((v >> 2) | (c << (2 * (K - 1))));
+        int flip = 0;
+        if (canonical) {
+          const unsigned long long rc = revcomp(w, K);
+          if (rc < w) { w = rc; flip = 1; }
+        }
+        const uint32_t bq = (uint32_t)(w >> key_bits);
+        const unsigned long long kq = w & kmask;
+        uint32_t a = offs[bq], e = offs[bq + 1];
+        while (a < e) {
+          const uint32_t mid = (a + e) >> 1;
+          if ((unsigned long long)keys[mid] < kq) a = mid + 1; else e = mid;
+        }
+        const bool found = a < offs[bq + 1] && (unsigned long long)keys[a] == kq;
+        out[(size_t)i * 8 + d] = found ? (int32_t)((a << 1) | (uint32_t)flip) : -1;
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace kmsc
 
@@ -136,5 +178,27 @@ static int spss_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* t
   PipelineResult res;
   KMSC_TRY(run_kmer_pipeline(ctx, in, opt, &res));
   *out = res.set;
+  return KMSC_OK;
+}
+
+extern "C" int kmsc_set_neighbors(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int32_t* out) {
+  if (!ctx || !set || (set->n_keys > 0 && !out)) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  if (set->n_keys >= ((int64_t)1 << 30)) { set_error("set too large for a neighbour table (%lld keys)", (long long)set->n_keys); return KMSC_E_INVALID; }
+  if (set->n_keys == 0) return KMSC_OK;
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  KMSC_TRY(ctx->work3.reserve((size_t)set->n_keys * 8 * sizeof(int32_t)));
+  int32_t* d_out = (int32_t*)ctx->work3.p;
+  const int nb = 1 << set->N;
+  int blocks = (nb + 7) / 8;
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  switch (set->key_bytes) {
+    case 2: neighbors_kernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>((const uint16_t*)set->keys, set->lev[0], nb, set->K, set->key_bits, canonical, d_out); break;
+    case 4: neighbors_kernel<uint32_t><<<blocks, 256, 0, ctx->stream>>>((const uint32_t*)set->keys, set->lev[0], nb, set->K, set->key_bits, canonical, d_out); break;
+    default: neighbors_kernel<unsigned long long><<<blocks, 256, 0, ctx->stream>>>((const unsigned long long*)set->keys, set->lev[0], nb, set->K, set->key_bits, canonical, d_out); break;
+  }
+  count_launch(ctx);
+  KMSC_CUDA(cudaGetLastError());
+  KMSC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)set->n_keys * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
   return KMSC_OK;
 }

@@ -5,10 +5,10 @@
 //  * GetSPSS / GetSPSSCanonical: construction (reference lib/core/spss.h:230-1858) is a
 //    "next" row and stays on the host. The reference builds unitigs and then
 //    a greedy path cover; any output that spells every k-mer of the set exactly once is
-//    valid (test/spss.cc:57-68, 113-124). This builder walks greedy simplitigs over
-//    the SORTED k-mer array (binary-search Contains, no hash tables): start at an
-//    unvisited k-mer, extend right while an unvisited successor exists, then left.
-//    Output is deterministic for a given set.
+//    valid (test/spss.cc:57-68, 113-124). This builder asks the GPU for the de Bruijn
+//    neighbours of every k-mer (kmsc_set_neighbors: one binary search per neighbour, the
+//    Contains() calls that dominate the reference) and walks greedy simplitigs over that
+//    table on the host. Output is deterministic for a given set.
 #ifndef KMSC_HOST_SPSS_H_
 #define KMSC_HOST_SPSS_H_
 #include <algorithm>
@@ -36,54 +36,60 @@ inline std::string Complement(std::string s) {
   return s;
 }
 
+// Greedy simplitigs over the device-computed neighbour table (kmsc_set_neighbors): start at an
+// unvisited k-mer, extend right while an unvisited successor exists (bases tried in A, C, G, T
+// order), then left. The walk keeps (k-mer index, orientation): orientation 1 means the string
+// spells the reverse complement of the stored (canonical) k-mer, whose successors are the
+// complemented predecessors of the stored one. Output is deterministic for a given set.
 template <int K, int N, typename KeyType>
 std::vector<std::string> BuildSPSS(const KmerSet<K, N, KeyType>& kmer_set, bool canonical) {
   const std::vector<std::uint64_t>& a = kmer_set.SortedBits();
-  std::vector<bool> visited(a.size(), false);
+  const std::size_t n = a.size();
   std::vector<std::string> out;
-  auto lookup = [&](const Kmer<K>& k) -> std::int64_t {
-    return internal::FindSorted(a, canonical ? k.Canonical().Bits() : k.Bits());
+  if (n == 0) return out;
+  std::vector<std::int32_t> nb(n * 8);
+  {
+    const SetPtr dev = kmer_set.Dev();
+    std::lock_guard<std::mutex> l(Device::Mu());
+    Device::Check(kmsc_set_neighbors(Device::Ctx(), dev->set, canonical ? 1 : 0, nb.data()), "kmsc_set_neighbors");
+  }
+  std::vector<bool> visited(n, false);
+  // oriented neighbour of (i, o) when base c is appended (right = true) or prepended
+  auto step = [&](std::size_t i, int o, int c, bool right, std::size_t* j, int* o2) -> bool {
+    std::int32_t e;
+    if (o == 0) e = nb[i * 8 + (right ? 0 : 4) + static_cast<std::size_t>(c)];
+    else e = nb[i * 8 + (right ? 4 : 0) + static_cast<std::size_t>(3 - c)];
+    if (e < 0) return false;
+    *j = static_cast<std::size_t>(e >> 1);
+    *o2 = o == 0 ? (e & 1) : !(e & 1);
+    return true;
   };
   std::string left;  // bases prepended while walking left (reversed)
-  for (std::size_t start = 0; start < a.size(); start++) {
+  for (std::size_t start = 0; start < n; start++) {
     if (visited[start]) continue;
     visited[start] = true;
-    const Kmer<K> first(a[start]);
-    std::string s = first.String();
-    // extend to the right
-    Kmer<K> cur = first;
-    for (;;) {
-      bool moved = false;
-      for (char c : {'A', 'C', 'G', 'T'}) {
-        const Kmer<K> nxt = cur.Next(c);
-        const std::int64_t idx = lookup(nxt);
-        if (idx >= 0 && !visited[static_cast<std::size_t>(idx)]) {
-          visited[static_cast<std::size_t>(idx)] = true;
-          s.push_back(c);
-          cur = nxt;
-          moved = true;
-          break;
+    std::string s = Kmer<K>(a[start]).String();
+    for (int dir = 0; dir < 2; dir++) {
+      const bool right = dir == 0;
+      left.clear();
+      std::size_t cur = start;
+      int o = 0;
+      for (;;) {
+        bool moved = false;
+        for (int c = 0; c < 4; c++) {
+          std::size_t j;
+          int o2;
+          if (step(cur, o, c, right, &j, &o2) && !visited[j]) {
+            visited[j] = true;
+            (right ? s : left).push_back("ACGT"[c]);
+            cur = j;
+            o = o2;
+            moved = true;
+            break;
+          }
         }
+        if (!moved) break;
       }
-      if (!moved) break;
-    }
-    // extend to the left
-    left.clear();
-    cur = first;
-    for (;;) {
-      bool moved = false;
-      for (char c : {'A', 'C', 'G', 'T'}) {
-        const Kmer<K> prv = cur.Prev(c);
-        const std::int64_t idx = lookup(prv);
-        if (idx >= 0 && !visited[static_cast<std::size_t>(idx)]) {
-          visited[static_cast<std::size_t>(idx)] = true;
-          left.push_back(c);
-          cur = prv;
-          moved = true;
-          break;
-        }
-      }
-      if (!moved) break;
     }
     if (!left.empty()) {
       std::reverse(left.begin(), left.end());

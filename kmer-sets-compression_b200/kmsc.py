@@ -30,7 +30,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.kmsc_count_reads.argtypes = L.kmsc_count_fasta.argtypes
     L.kmsc_count_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     L.kmsc_count_last_counts.argtypes = [C.c_void_p, _u8p, C.c_int64]
+    L.kmsc_set_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
     L.kmsc_set_bucket_offsets.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, _i64p]
     L.kmsc_set_export_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.kmsc_set_import_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -277,6 +278,11 @@ class Context:
         return out
 
     # -- P4 -------------------------------------------------------------------------
+    def set_neighbors(self, s: DeviceSet, canonical=True) -> np.ndarray:
+        out = np.zeros((max(1, s.n_keys), 8), np.int32)
+        _check(lib().kmsc_set_neighbors(self.h, s.h, int(canonical), out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out[: s.n_keys]
+
     # -- multi-GPU exchange helpers ---------------------------------------------------------
     def set_bucket_offsets(self, s: DeviceSet, buckets) -> np.ndarray:
         b = np.ascontiguousarray(buckets, np.int32)

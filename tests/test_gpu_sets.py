@@ -196,3 +196,25 @@ def test_export_import_bucket_ranges(ctx, oracle):
     # intersection counts add up over the ranges (what the all-reduce relies on)
     total = sum(int(ctx.pair_counts([p, s])[0, 1]) for p in parts)
     assert total == len(km)
+
+
+@pytest.mark.parametrize("K,N,canonical", [(15, 14, True), (23, 14, True), (31, 14, True), (9, 10, False), (5, 3, True)])
+def test_neighbor_table(ctx, oracle, K, N, canonical):
+    """kmsc_set_neighbors vs Kmer::Next / Prev / Canonical (reference lib/core/kmer.h:133-186) + set lookup"""
+    import synth
+    km = synth.kmer_set_of(synth.random_genome(3000, K), K, canonical=canonical)
+    offs, keys = synth.csr_of(km, K, N, KB[K])
+    s = ctx.set_from_csr(K, N, KB[K], offs, keys)
+    nb = ctx.set_neighbors(s, canonical=canonical)
+    index = {int(v): i for i, v in enumerate(km)}
+    rng = np.random.default_rng(K)
+    for i in rng.integers(0, len(km), 300):
+        v = int(km[i])
+        for c in range(4):
+            for d, w in ((0, oracle.next(v, K, "ACGT"[c])), (4, oracle.prev(v, K, "ACGT"[c]))):
+                q, flip = w, 0
+                if canonical:
+                    q = oracle.canonical(w, K)
+                    flip = int(q != w)
+                want = (index[q] << 1 | flip) if q in index else -1
+                assert nb[i, d + c] == want, (i, d, c)
