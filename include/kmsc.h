@@ -159,6 +159,14 @@ int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8);
  * pointer may be NULL. Inputs must be duplicate-free (true sets). */
 int kmsc_pair_split(kmsc_ctx* ctx, const kmsc_set* j, const kmsc_set* k, kmsc_set** inter,
                     kmsc_set** j_minus, kmsc_set** k_minus);
+/* The same for m pairs in ONE streaming pass (every input key read once, every output key
+ * written once): the n-1 tree edges of the `mst` driver, or one greedy iteration. All sets share
+ * (K, N, KeyType). inter / j_minus / k_minus: arrays of m handles, or NULL for an output that is
+ * not wanted. inter_hint (may be NULL): inter_hint[p] = |js[p] & ks[p]| if the caller knows it
+ * (kmsc_pair_counts over all buckets gives it); the outputs are then allocated exactly and
+ * written directly. A wrong hint costs a second pass for that pair, never a wrong result. */
+int kmsc_pair_split_batch(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* const* ks, int32_t m,
+                          const int64_t* inter_hint, kmsc_set** inter, kmsc_set** j_minus, kmsc_set** k_minus);
 /* KmerSet::Add(other) (lib/core/kmer_set.h:164-174) over m sets: the union that
  * KmerSetSet::Get / KmerSetSetReader::Get build (kmer_set_set.h:433-454, 672-755). */
 int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_set** out);

@@ -276,44 +276,6 @@ using namespace kmsc;
 
 extern "C" {
 
-int kmsc_pair_split(kmsc_ctx* ctx, const kmsc_set* j, const kmsc_set* k, kmsc_set** inter,
-                    kmsc_set** j_minus, kmsc_set** k_minus) {
-  if (!ctx) { set_error("ctx is NULL"); return KMSC_E_INVALID; }
-  KMSC_TRY(check_pair(j, k));
-  KMSC_CUDA(cudaSetDevice(ctx->device));
-  MergePlan mp;
-  uint32_t tot[3];
-  KMSC_TRY(merge_count(ctx, j, k, &mp, false, tot));
-  kmsc_set *sI = nullptr, *sA = nullptr, *sB = nullptr;
-  int rc = KMSC_OK;
-  {
-    int64_t nk[3]; uint32_t* src[3]; kmsc_set* made[3]; kmsc_set** dst[3];
-    int cnt = 0;
-    if (inter) { nk[cnt] = tot[0]; src[cnt] = mp.cI; dst[cnt++] = &sI; }
-    if (j_minus) { nk[cnt] = tot[1]; src[cnt] = mp.cA; dst[cnt++] = &sA; }
-    if (k_minus) { nk[cnt] = tot[2]; src[cnt] = mp.cB; dst[cnt++] = &sB; }
-    if (cnt > 0) {
-      rc = sets_from_fine_offsets(ctx, j, cnt, nk, src, mp.NF, made);
-      if (rc == KMSC_OK) for (int q = 0; q < cnt; q++) *dst[q] = made[q];
-    }
-  }
-  if (rc == KMSC_OK) {
-    dispatch_classify(ctx, true, j, k, mp, sI ? sI->keys : nullptr, sA ? sA->keys : nullptr,
-                      sB ? sB->keys : nullptr, nullptr);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = cuda_fail(e, "pair_split write", __FILE__, __LINE__);
-  }
-  if (rc != KMSC_OK) {
-    kmsc_set_free(ctx, sI); kmsc_set_free(ctx, sA); kmsc_set_free(ctx, sB);
-    return rc;
-  }
-  if (inter) *inter = sI;
-  if (j_minus) *j_minus = sA;
-  if (k_minus) *k_minus = sB;
-  return KMSC_OK;
-}
-
 int kmsc_set_diff(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, int64_t* diff) {
   if (!ctx || !diff) { set_error("NULL argument"); return KMSC_E_INVALID; }
   KMSC_TRY(check_pair(a, b));

@@ -31,7 +31,7 @@ EXPORTS = [
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
     "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
-    "kmsc_pair_split", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
+    "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
 ]
@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
                                         C.c_int32, _i64p]
     L.kmsc_pair_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.kmsc_pair_split_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, _i64p,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.kmsc_set_union.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
     L.kmsc_set_diff.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i64p]
     L.kmsc_count_fasta.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
@@ -302,6 +304,19 @@ class Context:
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib().kmsc_pair_split(self.h, j.h, k.h, C.byref(a) if want_inter else None, C.byref(b), C.byref(c)))
         return (DeviceSet(self, a.value) if want_inter else None), DeviceSet(self, b.value), DeviceSet(self, c.value)
+
+    def pair_split_batch(self, js, ks, inter_hint=None, want_inter=True, want_j=True, want_k=True):
+        """m pairs in one streaming pass -> (inter, j_minus, k_minus), each a list of m sets or None."""
+        m = len(js)
+        assert len(ks) == m
+        arrs = [(C.c_void_p * m)() if w else None for w in (want_inter, want_j, want_k)]
+        hint = None
+        if inter_hint is not None:
+            hint = np.ascontiguousarray(inter_hint, dtype=np.int64)
+            assert hint.shape == (m,)
+        _check(lib().kmsc_pair_split_batch(self.h, self._handles(js), self._handles(ks), m,
+                                           hint.ctypes.data_as(_i64p) if hint is not None else None, *arrs))
+        return tuple([DeviceSet(self, a[i]) for i in range(m)] if a is not None else None for a in arrs)
 
     def set_union(self, sets) -> DeviceSet:
         h = C.c_void_p()

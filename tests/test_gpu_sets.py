@@ -164,6 +164,91 @@ def test_split_empty_and_disjoint(ctx, oracle):
     assert np.array_equal(i.to_kmers(), a) and x.Size() == 0 and y.Size() == 0
 
 
+def _check_split(ctx, oracle, K, N, pairs_km, hint, want=(True, True, True)):
+    dj = [ctx.set_from_kmers(K, N, KB[K], a) for a, _ in pairs_km]
+    dk = [ctx.set_from_kmers(K, N, KB[K], b) for _, b in pairs_km]
+    inter, jm, km = ctx.pair_split_batch(dj, dk, inter_hint=hint, want_inter=want[0], want_j=want[1], want_k=want[2])
+    for p, (a, b) in enumerate(pairs_km):
+        wi = oracle.set_intersection(a, b)
+        if want[0]:
+            assert np.array_equal(inter[p].to_kmers(), wi), f"pair {p}: intersection"
+            assert inter[p].Hash() == oracle.set_hash(wi)
+        if want[1]:
+            assert np.array_equal(jm[p].to_kmers(), oracle.set_sub(a, wi)), f"pair {p}: j minus"
+        if want[2]:
+            assert np.array_equal(km[p].to_kmers(), oracle.set_sub(b, wi)), f"pair {p}: k minus"
+    # the offset levels of the new sets are exact: P3 over them gives the set algebra back
+    if all(want) and len(pairs_km) >= 1:
+        w = ctx.pair_counts([inter[0], jm[0], km[0], dj[0], dk[0]])
+        n = len(oracle.set_intersection(*pairs_km[0]))
+        assert w[0, 1] == 0 and w[0, 2] == 0 and w[1, 2] == 0 and w[0, 3] == n and w[0, 4] == n
+        assert w[1, 3] == len(pairs_km[0][0]) - n and w[2, 4] == len(pairs_km[0][1]) - n
+
+
+@pytest.mark.parametrize("K,N", [(15, 14), (23, 14), (31, 14), (19, 10)])
+def test_pair_split_batch(ctx, oracle, K, N):
+    """kmsc_pair_split_batch: several pairs per pass, with and without |j & k| hints (right and
+    wrong), any subset of outputs; reference semantics kmer_set_set.h:332-343"""
+    import synth
+    seqs = synth.phylogeny_sequences(6, 60000, p=0.01, seed=100 + K)
+    ks = [synth.kmer_set_of(s, K) for s in seqs]
+    e = np.zeros(0, np.uint64)
+    pairs = [(ks[0], ks[1]), (ks[2], ks[0]), (ks[3], ks[3]), (ks[4], e), (e, ks[5]), (e, e), (ks[1], ks[5][::3].copy())]
+    exact = np.array([len(oracle.set_intersection(a, b)) for a, b in pairs], np.int64)
+    _check_split(ctx, oracle, K, N, pairs, None)
+    _check_split(ctx, oracle, K, N, pairs, exact)
+    wrong = exact.copy()
+    wrong[0] = max(0, wrong[0] - 7); wrong[2] += 5; wrong[6] = 1 << 40; wrong[1] = -1
+    _check_split(ctx, oracle, K, N, pairs, wrong)
+    _check_split(ctx, oracle, K, N, pairs[:3], exact[:3], want=(False, True, True))
+    _check_split(ctx, oracle, K, N, pairs[:3], None, want=(True, False, False))
+
+
+def test_pair_split_dense_runs(ctx, oracle):
+    """keys concentrated in a few fine buckets: chunks that need several rounds, and single fine
+    buckets larger than the shared-memory tile (one-thread path)"""
+    K, N = 23, 14
+    rng = np.random.default_rng(5)
+
+    def cluster(prefix20, n):  # n distinct 46-bit values sharing their top 20 bits = one finest fine bucket
+        low = rng.choice(1 << 26, size=n, replace=False).astype(np.uint64)
+        return (np.uint64(prefix20) << np.uint64(26)) | low
+
+    base = np.concatenate([cluster(5, 3000), cluster(6, 3500), cluster(7, 2500), cluster(9, 12000), cluster(4000, 30000),
+                           rng.choice(1 << 46, size=20000, replace=False).astype(np.uint64)])
+    base = np.unique(base)
+    a = base[rng.random(len(base)) < 0.9]
+    b = base[rng.random(len(base)) < 0.8]
+    c = np.unique(np.concatenate([cluster(9, 9000), cluster(4000, 100), a[::7]]))
+    pairs = [(a, b), (b, c), (c, a)]
+    _check_split(ctx, oracle, K, N, pairs, None)
+    exact = np.array([len(oracle.set_intersection(x, y)) for x, y in pairs], np.int64)
+    _check_split(ctx, oracle, K, N, pairs, exact)
+
+
+def test_pair_split_full_size_properties(ctx):
+    """BASELINE config 2 sizes (10 M canonical 23-mers per set): size-independent properties --
+    |n| = W[j][k] from P3, |j\\n| = |j| - |n|, hash(n) ^ hash(j\\n) = hash(j), outputs disjoint"""
+    import synth
+    K, N = 23, 14
+    seqs = synth.phylogeny_sequences(3, 10_000_000 + K - 1, p=0.002, seed=9)
+    sets = [ctx.set_from_spss(K, N, 4, [synth.to_ascii(s).decode()]) for s in seqs]
+    W = ctx.pair_counts(sets)
+    js, ks = [sets[0], sets[0], sets[1]], [sets[1], sets[2], sets[2]]
+    hint = np.array([W[0, 1], W[0, 2], W[1, 2]], np.int64)
+    for h in (hint, None):
+        inter, jm, km = ctx.pair_split_batch(js, ks, inter_hint=h)
+        for p in range(3):
+            assert inter[p].Size() == hint[p]
+            assert jm[p].Size() == js[p].Size() - hint[p] and km[p].Size() == ks[p].Size() - hint[p]
+            assert inter[p].Hash() ^ jm[p].Hash() == js[p].Hash()
+            assert inter[p].Hash() ^ km[p].Hash() == ks[p].Hash()
+            w = ctx.pair_counts([inter[p], jm[p], km[p]])
+            assert w[0, 1] == 0 and w[0, 2] == 0 and w[1, 2] == 0
+            for s in (inter[p], jm[p], km[p]):
+                s.free()
+
+
 def test_export_import_bucket_ranges(ctx, oracle):
     """multi-GPU exchange helpers: a set cut into bucket ranges, every range exported to device
     buffers and imported as a restricted set; the ranges partition the set exactly"""
