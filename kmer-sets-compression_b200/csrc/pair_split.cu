@@ -9,17 +9,19 @@
 // split_stream_kernel: one CTA = 256 consecutive finest-level fine buckets of one pair, one thread
 // per fine bucket (about 10 + 10 keys). Units are handed out by a ticket counter.
 //   1. the thread merges its two runs straight from global memory (each run is a few sectors that
-//      stay in L1) and remembers which keys are common in two 64-bit masks;
+//      stay in L1) and remembers which keys are common in two 32-bit masks;
 //   2. a block scan of the per-bucket match counts gives the outputs' finest offsets inside the
 //      chunk and the chunk's totals;
 //   3. the totals go through a decoupled look-back over the earlier chunks of the same pair (one
 //      64-bit word per output: flag | count), so the global position of every output key is
 //      known without a counting pass and without a device-wide scan;
-//   4. the thread writes its keys from the masks (runs longer than 64 keys merge again) and
+//   4. the thread writes its keys from the masks (runs longer than 32 keys merge again) and
 //      every offset level of the up to three new sets that has an entry at its fine bucket.
-// A shared-memory tile version (coalesced tile loads, per-key binary search, warp-ballot
-// compaction in place) was measured 2-3 x slower: 4.3-7.2 warp instructions per key against
-// ~1 here (tools/experiments/pair_split_smem_tile.cu.txt, profiles/r01_p4_notes.md).
+// Measured alternatives (profiles/r01_p4_notes.md): a shared-memory tile version (coalesced tile
+// loads, per-key binary search, warp-ballot compaction in place) was 2-3 x slower (4.3-7.2 warp
+// instructions per key against 2.2 here; tools/experiments/pair_split_smem_tile.cu.txt); staging
+// each warp's runs in shared memory with 16-byte loads changed nothing (the kernel waits on the
+// look-back barrier and on instruction issue, not on L1).
 //
 // Output sizes are not known before the pass: with a caller-supplied |j & k| (the pair-counts
 // matrix has it) the outputs are allocated exactly and written directly; without it they are
@@ -34,6 +36,9 @@
 
 namespace kmsc {
 
+#ifndef KMSC_SPLIT_MINB
+#define KMSC_SPLIT_MINB 8   // resident CTAs per SM the register budget is cut for (32 registers)
+#endif
 constexpr int kSpThreads = 256;
 
 struct SplitPair {
@@ -69,7 +74,7 @@ __device__ __forceinline__ void write_levels(uint32_t* __restrict__ base, int N,
 // One CTA = 256 consecutive finest-level fine buckets of one pair, one thread per fine bucket.
 // Units are handed out by a ticket so that a unit only ever waits for units taken earlier.
 template <typename KeyT>
-__global__ void __launch_bounds__(kSpThreads) split_stream_kernel(
+__global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kernel(
     const SplitPair* __restrict__ pairs, uint32_t chunks_per_pair, uint32_t NF, int N, int F,
     unsigned long long* __restrict__ state, uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
   __shared__ uint32_t s_w[kSpThreads / 32];
@@ -88,20 +93,20 @@ __global__ void __launch_bounds__(kSpThreads) split_stream_kernel(
   const uint32_t x0 = c * kSpThreads, x = x0 + tid;
   const uint32_t xe = min(x0 + kSpThreads, NF);
   const bool live = x < NF;
-  // ---- pass 1: merge the two runs, remember which keys are common (runs of <= 64 keys) -----------
+  // ---- pass 1: merge the two runs, remember which keys are common (runs of <= 32 keys) -----------
   uint32_t i0 = 0, i1 = 0, j0 = 0, j1 = 0;
   if (live) { i0 = la[x]; i1 = la[x + 1]; j0 = lb[x]; j1 = lb[x + 1]; }
   const uint32_t A0 = la[x0], B0 = lb[x0], A1 = la[xe], B1 = lb[xe];
-  const bool small = (i1 - i0 <= 64) && (j1 - j0 <= 64);
-  unsigned long long mA = 0, mB = 0;
+  const bool small = (i1 - i0 <= 32) && (j1 - j0 <= 32);
+  uint32_t mA = 0, mB = 0;  // bit r: key r of the run is common (exact for runs of <= 32 keys)
   uint32_t nI = 0;
   {
     uint32_t i = i0, j = j0;
     while (i < i1 && j < j1) {
       const KeyT a = ka[i], b = kb[j];
       if (a == b) {
-        mA |= 1ull << ((i - i0) & 63);
-        mB |= 1ull << ((j - j0) & 63);
+        mA |= 1u << ((i - i0) & 31);
+        mB |= 1u << ((j - j0) & 31);
         nI++;
       }
       i += (a <= b);
@@ -183,19 +188,32 @@ __global__ void __launch_bounds__(kSpThreads) split_stream_kernel(
   uint32_t pI = s_g[0] + preI;
   uint32_t pA = s_g[1] + (i0 - A0) - preI;
   uint32_t pB = s_g[2] + (j0 - B0) - preI;
-  if (P->lev[0]) write_levels(P->lev[0], N, F, x, pI);
-  if (P->lev[1]) write_levels(P->lev[1], N, F, x, pA);
-  if (P->lev[2]) write_levels(P->lev[2], N, F, x, pB);
+  {
+    uint32_t* const l0 = P->lev[0];
+    uint32_t* const l1 = P->lev[1];
+    uint32_t* const l2 = P->lev[2];
+    const int tz = x ? min(F, __ffs(x) - 1) : F;  // levels F, F-1, ..., F-tz have an entry at x
+    size_t start = ((size_t)1 << N) * (((size_t)1 << F) - 1) + (size_t)F;
+    for (int sh = 0; sh <= tz; sh++) {
+      const size_t idx = start + (x >> sh);
+      if (l0) l0[idx] = pI;
+      if (l1) l1[idx] = pA;
+      if (l2) l2[idx] = pB;
+      start -= ((size_t)1 << (N + F - sh - 1)) + 1;  // level f - 1 starts 2^(N+f-1) + 1 entries earlier
+    }
+  }
   if (small) {
     const uint32_t lenA = i1 - i0, lenB = j1 - j0;
-    if (oI) for (unsigned long long m = mA; m; m &= m - 1) { if (pI < capI) oI[pI] = ka[i0 + __ffsll((long long)m) - 1]; pI++; }
+    const KeyT* const srcA = ka + i0;  // (the runs are still in L1 / L2)
+    const KeyT* const srcB = kb + j0;
+    if (oI) for (uint32_t m = mA; m; m &= m - 1) { if (pI < capI) oI[pI] = srcA[__ffs(m) - 1]; pI++; }
     if (oA) {
-      unsigned long long m = ~mA & (lenA >= 64 ? ~0ull : ((1ull << lenA) - 1ull));
-      for (; m; m &= m - 1) { if (pA < capA) oA[pA] = ka[i0 + __ffsll((long long)m) - 1]; pA++; }
+      uint32_t m = ~mA & (lenA >= 32 ? ~0u : ((1u << lenA) - 1u));
+      for (; m; m &= m - 1) { if (pA < capA) oA[pA] = srcA[__ffs(m) - 1]; pA++; }
     }
     if (oB) {
-      unsigned long long m = ~mB & (lenB >= 64 ? ~0ull : ((1ull << lenB) - 1ull));
-      for (; m; m &= m - 1) { if (pB < capB) oB[pB] = kb[j0 + __ffsll((long long)m) - 1]; pB++; }
+      uint32_t m = ~mB & (lenB >= 32 ? ~0u : ((1u << lenB) - 1u));
+      for (; m; m &= m - 1) { if (pB < capB) oB[pB] = srcB[__ffs(m) - 1]; pB++; }
     }
   } else {  // a run longer than the masks: merge again
     uint32_t i = i0, j = j0;

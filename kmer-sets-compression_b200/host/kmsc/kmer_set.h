@@ -111,18 +111,42 @@ class KmerSet {
     return static_cast<std::size_t>(h);
   }
 
-  // n = j & k, j \ n, k \ n in one device pass (reference kmer_set_set.h:332-343)
-  static void Split(const KmerSet& j, const KmerSet& k, KmerSet* inter, KmerSet* j_minus, KmerSet* k_minus) {
-    kmsc_set *a = nullptr, *b = nullptr, *c = nullptr;
-    const SetPtr dj = j.Dev(), dk = k.Dev();
+  // n = j & k, j \ n, k \ n in one device pass (reference kmer_set_set.h:332-343).
+  // inter_size: |j & k| if the caller knows it exactly (an all-bucket weight), else -1.
+  static void Split(const KmerSet& j, const KmerSet& k, KmerSet* inter, KmerSet* j_minus, KmerSet* k_minus,
+                    std::int64_t inter_size = -1) {
+    std::vector<KmerSet> a, b, c;
+    SplitBatch({&j}, {&k}, inter_size >= 0 ? std::vector<std::int64_t>{inter_size} : std::vector<std::int64_t>{},
+               inter ? &a : nullptr, j_minus ? &b : nullptr, k_minus ? &c : nullptr);
+    if (inter) *inter = a[0];
+    if (j_minus) *j_minus = b[0];
+    if (k_minus) *k_minus = c[0];
+  }
+  // the same for m pairs in one streaming pass (kmsc_pair_split_batch); inter_sizes empty or one per pair
+  static void SplitBatch(const std::vector<const KmerSet*>& js, const std::vector<const KmerSet*>& ks,
+                         const std::vector<std::int64_t>& inter_sizes, std::vector<KmerSet>* inter,
+                         std::vector<KmerSet>* j_minus, std::vector<KmerSet>* k_minus) {
+    const std::size_t m = js.size();
+    std::vector<SetPtr> hold;
+    std::vector<const kmsc_set*> hj(m), hk(m);
+    for (std::size_t p = 0; p < m; p++) {
+      hold.push_back(js[p]->Dev()); hj[p] = hold.back()->set;
+      hold.push_back(ks[p]->Dev()); hk[p] = hold.back()->set;
+    }
+    std::vector<kmsc_set*> a(inter ? m : 0), b(j_minus ? m : 0), c(k_minus ? m : 0);
     {
       std::lock_guard<std::mutex> l(Device::Mu());
-      Device::Check(kmsc_pair_split(Device::Ctx(), dj->set, dk->set, inter ? &a : nullptr,
-                                    j_minus ? &b : nullptr, k_minus ? &c : nullptr), "kmsc_pair_split");
+      Device::Check(kmsc_pair_split_batch(Device::Ctx(), hj.data(), hk.data(), static_cast<std::int32_t>(m),
+                                          inter_sizes.size() == m && m > 0 ? inter_sizes.data() : nullptr,
+                                          inter ? a.data() : nullptr, j_minus ? b.data() : nullptr,
+                                          k_minus ? c.data() : nullptr), "kmsc_pair_split_batch");
     }
-    if (inter) inter->Adopt(a);
-    if (j_minus) j_minus->Adopt(b);
-    if (k_minus) k_minus->Adopt(c);
+    auto adopt = [m](std::vector<KmerSet>* out, std::vector<kmsc_set*>& h) {
+      if (!out) return;
+      out->assign(m, KmerSet());
+      for (std::size_t p = 0; p < m; p++) (*out)[p].Adopt(h[p]);
+    };
+    adopt(inter, a); adopt(j_minus, b); adopt(k_minus, c);
   }
 
   // device handle, uploading the host vector if needed

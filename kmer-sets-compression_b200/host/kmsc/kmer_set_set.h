@@ -137,7 +137,7 @@ class KmerSetSet {
       merges_.push_back({j, k, weight});
 
       Set inter, jm, km;
-      Set::Split(sets[j], sets[k], &inter, &jm, &km);
+      Set::Split(sets[j], sets[k], &inter, &jm, &km, opt.exact ? weight : -1);  // exact weight = |S_j & S_k|
       sets[j] = jm;
       sets[k] = km;
       sets.push_back(inter);
@@ -356,7 +356,7 @@ struct MstResult {
 
 // Minimum spanning tree of the symmetric-difference graph: edges sorted by
 // (d ascending, i ascending, j ascending), Kruskal with ParallelDisjointSet, tree
-// oriented by BFS from set 0, difference sets per edge from one device split each.
+// oriented by BFS from set 0, the difference sets of all edges from one batched device split.
 template <int K, int N, typename KeyType>
 MstResult<K, N, KeyType> BuildMst(const std::vector<KmerSet<K, N, KeyType>>& sets) {
   using Set = KmerSet<K, N, KeyType>;
@@ -391,13 +391,19 @@ MstResult<K, N, KeyType> BuildMst(const std::vector<KmerSet<K, N, KeyType>>& set
       if (seen[static_cast<std::size_t>(e.first)]) continue;
       seen[static_cast<std::size_t>(e.first)] = true;
       r.edges.push_back({p, e.first, e.second});
-      Set only_p, only_c;
-      Set::Split(sets[static_cast<std::size_t>(p)], sets[static_cast<std::size_t>(e.first)], nullptr, &only_p, &only_c);
-      r.del.push_back(only_p);
-      r.add.push_back(only_c);
       q.push(e.first);
     }
   }
+  // the difference sets of all n - 1 tree edges in one streaming device pass; the exact matrix
+  // gives every |S_p & S_c|, so the outputs are allocated exactly and written directly
+  std::vector<const Set*> js, ks;
+  std::vector<std::int64_t> inter_sizes;
+  for (const MstEdge& e : r.edges) {
+    js.push_back(&sets[static_cast<std::size_t>(e.parent)]);
+    ks.push_back(&sets[static_cast<std::size_t>(e.child)]);
+    inter_sizes.push_back(r.W[static_cast<std::size_t>(e.parent) * n + e.child]);
+  }
+  if (!r.edges.empty()) Set::SplitBatch(js, ks, inter_sizes, nullptr, &r.del, &r.add);
   return r;
 }
 
