@@ -152,6 +152,10 @@ int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
  * overflow, out[5] tile target L, out[6] main-kernel launches, out[7] algorithmic
  * bytes (keys * sizeof(KeyType) + offsets read + n*n*8). */
 int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8);
+/* Which build the main phase of the LAST kmsc_pair_counts* call used: 0 = shared-memory hash
+ * table (cost per key), 1 = warp-wide multiway merge (cost per distinct key; chosen for up to
+ * 128 related sets). Same results; the environment variable KMSC_P3_BUILD=hash|merge forces one. */
+int kmsc_pair_counts_build(kmsc_ctx* ctx);
 
 /* ---- P4: pair split / set algebra ------------------------------------------------ */
 /* Replaces kmer_set_set.h:332-343: n = Intersection(j, k); j.Sub(n); k.Sub(n)

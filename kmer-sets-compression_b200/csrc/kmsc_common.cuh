@@ -56,6 +56,7 @@ struct kmsc_ctx {
   int pc_rho_n = 0, pc_rho_k = 0;
   unsigned long long pc_last_stats[3] = {0, 0, 0};
   unsigned long long pc_last_L = 0;
+  int pc_last_build = 0;  // 0 hash build, 1 merge build
   cudaEvent_t pc_ev[3] = {nullptr, nullptr, nullptr};  // plan start, main start, main end
   double pc_main_ms = 0, pc_plan_ms = 0, pc_algo_bytes = 0;
   int pc_main_launches = 0;

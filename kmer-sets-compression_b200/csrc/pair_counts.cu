@@ -32,7 +32,8 @@ namespace kmsc {
 
 struct SetDesc {
   const void* keys;
-  const uint32_t* lev;  // fine offsets at the level chosen for this call
+  const uint32_t* lev;         // fine offsets at the level chosen for this call
+  const uint32_t* lev_finest;  // fine offsets at the set's finest level (merge build: segment bounds)
 };
 
 struct PlanParams {
@@ -771,6 +772,10 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
   }
 }
 
+}  // namespace kmsc
+#include "pair_counts_stream.cuh"
+namespace kmsc {
+
 // ---------------------------------------------------------------------------
 // exact merge fallback (sets with duplicate keys), reference loop :165-180
 // ---------------------------------------------------------------------------
@@ -857,6 +862,56 @@ static int launch_main(kmsc_ctx* ctx, const SetDesc* d_sets, int n_sets, const u
   return KMSC_OK;
 }
 
+// the merge build (pair_counts_stream.cuh): n <= 128 sets
+template <typename KeyT, int NS>
+static int launch_stream(kmsc_ctx* ctx, const SetDesc* d_sets, int n_sets, const uint32_t* d_offsT,
+                         const Tile* d_tiles, const uint32_t* d_ntiles, uint32_t* d_counter,
+                         unsigned long long* d_W, unsigned long long* d_stats, int fine_level, int finest_level,
+                         uint32_t max_tiles) {
+  using C = PmCfg<NS>;
+  const size_t smem = PmLayout<KeyT, NS>::total;
+  auto kern = pair_counts_stream_kernel<KeyT, NS>;
+  static int occ_cache[64] = {0};
+  int occ = ctx->device < 64 ? occ_cache[ctx->device] : 0;
+  if (occ == 0) {
+    KMSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    KMSC_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int smem_sm = 0, smem_res = 0, regs_sm = 0, thr_sm = 0;
+    KMSC_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, ctx->device));
+    occ = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + (size_t)smem_res));
+    const int regs_per_cta = ((fa.numRegs + 7) & ~7) * C::T;
+    if (regs_per_cta > 0) occ = std::min(occ, regs_sm / regs_per_cta);
+    occ = std::min(occ, thr_sm / C::T);
+    occ = std::min(occ, 512 / NS);  // tensor-memory columns
+    if (occ < 1) { set_error("pair_counts stream kernel does not fit on an SM (smem %zu, %d regs)", smem, fa.numRegs); return KMSC_E_CUDA; }
+    if (getenv("KMSC_DEBUG"))
+      fprintf(stderr, "[kmsc] pair_counts stream NS=%d T=%d smem=%zu regs=%d -> %d CTAs per SM\n", NS, C::T, smem, fa.numRegs, occ);
+    if (ctx->device < 64) occ_cache[ctx->device] = occ;
+  }
+  long long grid = (long long)ctx->sm_count * occ;
+  if (grid > (long long)max_tiles) grid = max_tiles;
+  if (grid < 1) grid = 1;
+  const int spw = (n_sets + NS / 8 - 1) / (NS / 8);  // sets per group of 8 Gram positions
+  kern<<<(unsigned)grid, C::T, smem, ctx->stream>>>(d_sets, n_sets, spw, d_offsT, d_tiles, d_ntiles, d_counter, d_W,
+                                                    d_stats, fine_level, finest_level);
+  count_launch(ctx);
+  KMSC_CUDA(cudaGetLastError());
+  return KMSC_OK;
+}
+
+template <typename KeyT>
+static int launch_stream_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_sets, const uint32_t* d_offsT,
+                            const Tile* d_tiles, const uint32_t* d_ntiles, uint32_t* d_counter,
+                            unsigned long long* d_W, unsigned long long* d_stats, int fine_level, int finest_level,
+                            uint32_t max_tiles) {
+  if (ns == 64) return launch_stream<KeyT, 64>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, fine_level, finest_level, max_tiles);
+  return launch_stream<KeyT, 128>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, fine_level, finest_level, max_tiles);
+}
+
 template <typename KeyT>
 static int launch_main_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_sets,
                           const uint32_t* d_offsT, const Tile* d_tiles, const uint32_t* d_ntiles,
@@ -885,7 +940,7 @@ struct PcDev {
 
 // One pass: plan tiles over the buckets selected by h_bitmap (NULL = all) with
 // tile target L, then run the main kernel accumulating into d_W.
-static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
+static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, bool merge_build,
                      const uint32_t* h_bitmap, unsigned long long L, double keys_in_phase,
                      unsigned long long* d_W, unsigned long long host_stats[4]) {
   const kmsc_set* s0 = sets[0];
@@ -923,7 +978,7 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
   void* pin = nullptr;
   KMSC_TRY(ctx_pinned(ctx, sz_desc + sz_bitmap + 64, &pin));
   SetDesc* h_sets = (SetDesc*)pin;
-  for (int i = 0; i < n; i++) { h_sets[i].keys = sets[i]->keys; h_sets[i].lev = sets[i]->lev[f]; }
+  for (int i = 0; i < n; i++) { h_sets[i].keys = sets[i]->keys; h_sets[i].lev = sets[i]->lev[f]; h_sets[i].lev_finest = sets[i]->lev[sets[i]->max_level]; }
   KMSC_CUDA(cudaMemsetAsync(sm, 0, 256, ctx->stream));
   KMSC_CUDA(cudaMemcpyAsync(d.sets, h_sets, sz_desc, cudaMemcpyHostToDevice, ctx->stream));
   if (h_bitmap) {
@@ -958,6 +1013,13 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns,
   }
   KMSC_CUDA(cudaEventRecord(ctx->pc_ev[1], ctx->stream));
   int rc;
+  if (merge_build) {
+    switch (s0->key_bytes) {
+      case 2: rc = launch_stream_ns<uint16_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles); break;
+      case 4: rc = launch_stream_ns<uint32_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles); break;
+      default: rc = launch_stream_ns<unsigned long long>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles); break;
+    }
+  } else
   switch (s0->key_bytes) {
     case 2: rc = launch_main_ns<uint16_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
     case 4: rc = launch_main_ns<uint32_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, s0->key_bits, f, max_tiles); break;
@@ -1090,7 +1152,7 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
     void* pin = nullptr;
     KMSC_TRY(ctx_pinned(ctx, sz_desc + sz_bitmap + 64, &pin));
     SetDesc* h_sets = (SetDesc*)pin;
-    for (int i = 0; i < n; i++) { h_sets[i].keys = sets[i]->keys; h_sets[i].lev = sets[i]->lev[0]; }
+    for (int i = 0; i < n; i++) { h_sets[i].keys = sets[i]->keys; h_sets[i].lev = sets[i]->lev[0]; h_sets[i].lev_finest = sets[i]->lev[sets[i]->max_level]; }
     KMSC_CUDA(cudaMemcpyAsync(d_sets, h_sets, sz_desc, cudaMemcpyHostToDevice, ctx->stream));
     if (bucket_ids) {
       memcpy((unsigned char*)pin + sz_desc, sel.data(), sz_bitmap);
@@ -1130,7 +1192,7 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
       if ((rank++ & 63) == 21) probe[b >> 5] |= 1u << (b & 31);
       else rest[b >> 5] |= 1u << (b & 31);
     }
-    KMSC_TRY(run_phase(ctx, sets, n, ns, probe.data(), L_cons, mean_bucket, d_W, st));
+    KMSC_TRY(run_phase(ctx, sets, n, ns, false, probe.data(), L_cons, mean_bucket, d_W, st));
     if (st[1] > 0) rho = (double)st[0] / (double)st[1];
     ctx->pc_last_stats[0] += st[0]; ctx->pc_last_stats[1] += st[1]; ctx->pc_last_stats[2] += st[2];
     phase2 = rest.data();
@@ -1140,8 +1202,27 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
     const unsigned long long La = (unsigned long long)(PC_LFRAC * rho * dmax);
     if (La > L) L = La;
   }
+  // Build choice: the hash build costs ~3.7 warp instructions per key, the merge build ~25 per
+  // distinct key and mask word pair = 25 (ns / 64) / rho per key (pair_counts_stream.cuh).
+  // KMSC_P3_BUILD=hash|merge overrides (tests run both).
+  bool merge_build = ns <= 128 && rho >= 8.0 * (ns / 64);
+  if (const char* e = getenv("KMSC_P3_BUILD")) {
+    if (!strcmp(e, "hash")) merge_build = false;
+    else if (!strcmp(e, "merge")) merge_build = ns <= 128;
+  }
+  if (merge_build) {
+    // no table to overflow (a full mask arena is flushed and the merge resumes): tiles of a few
+    // arena fills keep the per-set slices long (less block over-read at their ends) and amortise
+    // the end-of-tile imbalance between the warps
+    const double r = rho > 1.0 ? rho : 1.0;
+    double fills = 2.5;
+    if (const char* e = getenv("KMSC_P3_FILLS")) { const double v = atof(e); if (v > 0.1 && v < 64) fills = v; }
+    L = (unsigned long long)(fills * r * PmCfg<64>::SS);
+    if (L < L_cons) L = L_cons;
+  }
   if (L > L_max) L = L_max;
-  KMSC_TRY(run_phase(ctx, sets, n, ns, phase2, L, mean_bucket, d_W, st));
+  ctx->pc_last_build = merge_build ? 1 : 0;
+  KMSC_TRY(run_phase(ctx, sets, n, ns, merge_build, phase2, L, mean_bucket, d_W, st));
   if (st[1] > 0) {
     ctx->pc_rho = (double)st[0] / (double)st[1];
     ctx->pc_rho_n = n;
@@ -1188,6 +1269,8 @@ int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8) {
   out8[6] = (double)ctx->pc_main_launches; out8[7] = ctx->pc_algo_bytes;
   return KMSC_OK;
 }
+
+int kmsc_pair_counts_build(kmsc_ctx* ctx) { return ctx ? ctx->pc_last_build : -1; }
 
 int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                           const int32_t* rows, int32_t n_rows, const int32_t* bucket_ids,

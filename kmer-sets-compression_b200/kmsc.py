@@ -30,7 +30,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.kmsc_pair_counts_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, C.c_void_p]
     L.kmsc_pair_counts_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i32p,
                                         C.c_int32, _i64p]
+    L.kmsc_pair_counts_build.argtypes = [C.c_void_p]
     L.kmsc_pair_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.kmsc_pair_split_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, _i64p,
@@ -265,6 +266,10 @@ class Context:
             ids = np.ascontiguousarray(bucket_ids, np.int32)
             idp, nid = ids.ctypes.data_as(_i32p), len(ids)
         _check(lib().kmsc_pair_counts_device(self.h, self._handles(sets), n, idp, nid, C.c_void_p(d_out_ptr)))
+
+    def pair_counts_build(self) -> int:
+        """0 = hash build, 1 = merge build (main phase of the last pair_counts call)"""
+        return int(lib().kmsc_pair_counts_build(self.h))
 
     def pair_counts_rows(self, sets, rows, bucket_ids=None):
         n = len(sets)

@@ -22,6 +22,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(autouse=True, params=["hash", "merge"])
+def build(request, monkeypatch):
+    """every case runs with both builds of the main kernel (KMSC_P3_BUILD): the shared-memory
+    hash table and the warp-wide multiway merge give the same matrices"""
+    monkeypatch.setenv("KMSC_P3_BUILD", request.param)
+    return request.param
+
+
 def _mk_sets(ctx, oracle, kmer_sets, K, N, kb):
     import synth
     dev, offs_l, keys_l = [], [], []
@@ -36,6 +44,9 @@ def _mk_sets(ctx, oracle, kmer_sets, K, N, kb):
 def _check(ctx, oracle, kmer_sets, K, N, kb, bucket_ids=None):
     dev, offs_l, keys_l = _mk_sets(ctx, oracle, kmer_sets, K, N, kb)
     got, visits = ctx.pair_counts(dev, bucket_ids, with_visits=True)
+    import os
+    if any(len(k) for k in kmer_sets):
+        assert ctx.pair_counts_build() == (1 if os.environ["KMSC_P3_BUILD"] == "merge" and len(kmer_sets) <= 128 else 0)
     want, want_visits = oracle.pair_counts(offs_l, keys_l, kb, 1 << N, bucket_ids=bucket_ids, n_threads=8)
     n = len(kmer_sets)
     iu = np.triu_indices(n, 1)
