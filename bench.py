@@ -316,6 +316,7 @@ def main():
         main_launches += int(st["main_launches"])
     e1.record(stream)
     barrier()
+    p3_build = ctx.pair_counts_build()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
     ms = e0.elapsed_time(e1)
@@ -482,13 +483,16 @@ def main():
     # DRAM traffic of the dominant kernel per launch: from the committed ncu capture of this
     # workload (it cannot be measured outside a profiler); null for any other shape
     traffic = None
+    kernel_name = "pair_counts_stream_kernel" if p3_build == 1 else "pair_counts_kernel"
     try:
-        tr = json.loads((ROOT / "profiles" / "p3_traffic.json").read_text())
+        tr = json.loads((ROOT / "profiles" / "p3_traffic.json").read_text())["kernels"][kernel_name]
         if args.sets == 64 and args.kmers == 10_000_000 and K == 23:
             traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "pair_counts_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": kernel_name,
+                "build": "warp-wide multiway merge (related sets)" if p3_build == 1 else "shared-memory hash table",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": algo_bytes / max(1, main_launches),

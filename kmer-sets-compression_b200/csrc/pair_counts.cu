@@ -293,7 +293,7 @@ struct PcLayout {
 
 // misc[] slots
 constexpr int kMiscNdist = 0, kMiscOverflow = 1, kMiscTile = 2, kMiscSp = 3, kMiscSpecial = 4, kMiscTmem = 5,
-              kMiscAnyMma = 6, kMiscNext = 7, kMiscIns = 8;
+              kMiscAnyMma = 6, kMiscNext = 7, kMiscIns = 8, kMiscSeg = 9;
 
 // The table is probed two slots at a time: slots (h, h + 1) with h even are one 8 / 16-byte
 // load. Slow path, per lane (divergent, rare): neither slot of the home pair held the key
@@ -896,8 +896,12 @@ static int launch_stream(kmsc_ctx* ctx, const SetDesc* d_sets, int n_sets, const
   if (grid > (long long)max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
   const int spw = (n_sets + NS / 8 - 1) / (NS / 8);  // sets per group of 8 Gram positions
+  // prefetching the next tile into L2 (as the hash build does) costs this kernel time: its tiles
+  // are several buckets long, 444 CTAs' worth of next tiles exceed the L2 and are read twice
+  // (ncu r01: 5.4 GB of DRAM reads for 2.56 GB of keys with it). KMSC_P3_PF=1 turns it on.
+  const int l2_prefetch = getenv("KMSC_P3_PF") ? atoi(getenv("KMSC_P3_PF")) : 0;
   kern<<<(unsigned)grid, C::T, smem, ctx->stream>>>(d_sets, n_sets, spw, d_offsT, d_tiles, d_ntiles, d_counter, d_W,
-                                                    d_stats, fine_level, finest_level);
+                                                    d_stats, fine_level, finest_level, l2_prefetch);
   count_launch(ctx);
   KMSC_CUDA(cudaGetLastError());
   return KMSC_OK;
@@ -996,7 +1000,8 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, 
     // the table key: uint32 for 2/4-byte keys, uint64 for 8-byte keys
     const int tk_bits = s0->key_bytes == 8 ? 64 : 32;
     const int spare = tk_bits - s0->key_bits;
-    const uint32_t bucket_span = spare >= 8 ? 256u : (1u << spare);
+    // (the merge build has no table key: its tiles may always span buckets)
+    const uint32_t bucket_span = (spare >= 8 || merge_build) ? 256u : (1u << spare);
     const uint64_t span = (uint64_t)bucket_span << f;
     pp.span = span > 256 ? 256u : (uint32_t)span;
   }
@@ -1202,10 +1207,11 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
     const unsigned long long La = (unsigned long long)(PC_LFRAC * rho * dmax);
     if (La > L) L = La;
   }
-  // Build choice: the hash build costs ~3.7 warp instructions per key, the merge build ~25 per
-  // distinct key and mask word pair = 25 (ns / 64) / rho per key (pair_counts_stream.cuh).
+  // Build choice: the hash build costs ~3.7 warp instructions per key, the merge build ~51 per
+  // distinct key at ns = 64 (two sets per lane) = 51 (ns / 64) / rho per key (ncu r01,
+  // pair_counts_stream.cuh): break-even near rho = 14 ns / 64.
   // KMSC_P3_BUILD=hash|merge overrides (tests run both).
-  bool merge_build = ns <= 128 && rho >= 8.0 * (ns / 64);
+  bool merge_build = ns <= 128 && rho >= 14.0 * (ns / 64);
   if (const char* e = getenv("KMSC_P3_BUILD")) {
     if (!strcmp(e, "hash")) merge_build = false;
     else if (!strcmp(e, "merge")) merge_build = ns <= 128;
@@ -1215,7 +1221,7 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
     // arena fills keep the per-set slices long (less block over-read at their ends) and amortise
     // the end-of-tile imbalance between the warps
     const double r = rho > 1.0 ? rho : 1.0;
-    double fills = 2.5;
+    double fills = 8.0;
     if (const char* e = getenv("KMSC_P3_FILLS")) { const double v = atof(e); if (v > 0.1 && v < 64) fills = v; }
     L = (unsigned long long)(fills * r * PmCfg<64>::SS);
     if (L < L_cons) L = L_cons;

@@ -7,11 +7,13 @@
 // the head key of NS / 32 sets per lane, takes the minimum over the warp with one
 // redux.sync.min, and the ballots of "my head equals the minimum" ARE the membership mask of
 // that distinct key, straight in the bit order the Gram expects. No table, no CAS, no compaction
-// scan: about 25 warp instructions per distinct key = 25 / rho per key.
+// scan. Measured (ncu r01, C2, rho = 16.4): 51 warp instructions per distinct key = 3.1 per key
+// against 3.7 for the hash build, 3.23 ms against 3.58 ms; the break-even is near rho = 14.
 //
 //   tile     as planned by plan_* (a fine-bucket range holding ~L keys over all sets)
-//   segment  the tile's finest-level range cut into one piece per warp (never across a bucket:
-//            keys ascend inside a bucket only); the piece of every set is one contiguous key slice
+//   segment  the tile's finest-level range cut into about four pieces per warp (never across a
+//            bucket: keys ascend inside a bucket only), handed out by a counter; the piece of
+//            every set is one contiguous key slice
 //   ring     per (lane, set) a 16-key window in shared memory, filled by cp.async in 8-key
 //            blocks (global -> shared without registers). Every 4 iterations all lanes top their
 //            rings up in uniform code; the blocks land while the keys before them are merged
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(PmCfg<NS>::T, PmCfg<NS>::MINB)
 pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const uint32_t* __restrict__ offsT,
                           const Tile* __restrict__ tiles, const uint32_t* __restrict__ n_tiles_p,
                           uint32_t* __restrict__ tile_counter, unsigned long long* __restrict__ W,
-                          unsigned long long* __restrict__ stats, int fine_level, int finest_level) {
+                          unsigned long long* __restrict__ stats, int fine_level, int finest_level, int l2_prefetch) {
   using C = PmCfg<NS>;
   using LY = PmLayout<KeyT, NS>;
   using CmpT = typename TableKey<KeyT>::type;  // uint32 for 2/4-byte keys, uint64 for 8-byte keys
@@ -79,6 +81,7 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
   constexpr int MW = NS / 32;   // mask words per distinct key = sets per lane
   constexpr int NW = T / 32;
   constexpr int DW = SS / NW;   // mask slots per warp between two flushes
+  static_assert(DW % 4 == 0, "the arena-full test rides on the ring top-up");
   constexpr int MMA_M = NS == 64 ? 64 : 128;
   constexpr int MMA_N = NS;
   constexpr int TMEM_COLS = NS;
@@ -187,9 +190,11 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
         const Tile tn = tiles[t_nx];
         nx_b = offsT[(size_t)tn.x0 * n_sets + tid];
         nx_e = offsT[(size_t)tn.x1 * n_sets + tid];
-        const char* base = (const char*)skp[tid];
-        const size_t lo = ((size_t)nx_b * sizeof(KeyT)) & ~(size_t)127, hi = (size_t)nx_e * sizeof(KeyT);
-        for (size_t off = lo; off < hi; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        if (l2_prefetch) {
+          const char* base = (const char*)skp[tid];
+          const size_t lo = ((size_t)nx_b * sizeof(KeyT)) & ~(size_t)127, hi = (size_t)nx_e * sizeof(KeyT);
+          for (size_t off = lo; off < hi; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
       }
       sbeg[(par ^ 1) * NS + tid] = nx_b;
       send[(par ^ 1) * NS + tid] = nx_e;
@@ -198,12 +203,24 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
     const uint32_t X0 = tl.x0 << up, X1 = tl.x1 << up;
     const uint32_t bucket0 = X0 >> finest_level;
     const uint32_t nbk = ((X1 - 1) >> finest_level) - bucket0 + 1;
-    const uint32_t n_seg = nbk == 1 ? (uint32_t)NW : nbk;
-    uint32_t seg_next = (uint32_t)warp;
+    // every bucket part of the tile is cut into P pieces (a power of two) so that there are about
+    // four segments per warp; segments are taken from a counter (buckets differ in size)
+    uint32_t P = 1;
+    while (P * nbk < 4u * NW && P < (1u << finest_level)) P <<= 1;
+    const uint32_t n_seg = nbk * P;
+    if (tid == 0) misc[kMiscSeg] = 0;
+    __syncthreads();
+    auto take_seg = [&]() -> uint32_t {
+      uint32_t q = 0;
+      if (lane == 0) q = (uint32_t)atomicAdd(&misc[kMiscSeg], 1);
+      return __shfl_sync(0xffffffffu, q, 0);
+    };
+    uint32_t seg_next = take_seg();
     bool have_seg = false;
     // merge state of this warp's current segment (kept across flushes)
     uint32_t ci[MW], ce[MW];   // next key index / end of the slice, per set of this lane
     uint32_t clim[MW];         // keys below clim are in the ring or on their way (a multiple of 8)
+    const char* cptr[MW];      // address of key clim in the set's key array
     CmpT ck[MW];               // head key; KMAX once the slice is exhausted
     uint32_t cnt = 0;          // masks in this warp's arena
     for (uint32_t round = 0;; round++) {
@@ -211,21 +228,16 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
       while (!full) {
         if (!have_seg) {
           if (seg_next >= n_seg) break;
-          uint32_t xa, xb;
-          if (nbk == 1) {
-            const uint32_t len = X1 - X0;
-            xa = X0 + (uint32_t)(((unsigned long long)len * seg_next) / NW);
-            xb = X0 + (uint32_t)(((unsigned long long)len * (seg_next + 1)) / NW);
-          } else {
-            xa = max(X0, (bucket0 + seg_next) << finest_level);
-            xb = min(X1, (bucket0 + seg_next + 1) << finest_level);
-          }
-          seg_next += NW;
+          const uint32_t bk = bucket0 + seg_next / P, piece = seg_next % P;
+          const uint32_t B0 = max(X0, bk << finest_level), B1 = min(X1, (bk + 1) << finest_level);
+          const uint32_t xa = B0 + (uint32_t)(((unsigned long long)(B1 - B0) * piece) / P);
+          const uint32_t xb = B0 + (uint32_t)(((unsigned long long)(B1 - B0) * (piece + 1)) / P);
+          seg_next = take_seg();
           if (xa >= xb) continue;
           cp_async_wait<0>();  // nothing of the previous segment may still land in the rings
 #pragma unroll
           for (int j = 0; j < MW; j++) {
-            ci[j] = 0; ce[j] = 0; ck[j] = KMAX; clim[j] = 0;
+            ci[j] = 0; ce[j] = 0; ck[j] = KMAX; clim[j] = 0xffffffffu; cptr[j] = nullptr;  // (an empty slice never asks for keys)
             if (sidx[j] >= 0) {
               const uint32_t* lv = slev[sidx[j]];
               ci[j] = lv[xa];
@@ -236,6 +248,7 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
                 ring_fetch(j, kp, g0);
                 if (g0 + 8 < ce[j]) ring_fetch(j, kp, g0 + 8);
                 clim[j] = g0 + 16;
+                cptr[j] = kp + (size_t)(g0 + 16) * sizeof(KeyT);
               }
             }
           }
@@ -254,14 +267,17 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
         // ahead, of which >= 5 were asked for at an earlier top-up and have landed (wait_group 1),
         // so the block asked for now is not read before the next top-up has waited for it.
         for (;;) {
-          if (cnt == (uint32_t)DW) { full = true; break; }
           if ((cnt & 3u) == 0u) {
+            if (cnt == (uint32_t)DW) { full = true; break; }  // (DW is a multiple of 4)
 #pragma unroll
             for (int j = 0; j < MW; j++) {
               const uint32_t want = (ci[j] & ~7u) + 16u;  // the ring covers [block of ci, +16)
               if (clim[j] < want && clim[j] < ce[j]) {
-                ring_fetch(j, (const char*)skp[sidx[j]], clim[j]);
+                const uint32_t o = (clim[j] & 8u) * (uint32_t)sizeof(KeyT);  // first or second half of the slot
+#pragma unroll
+                for (uint32_t q = 0; q < BLKB / 16; q++) cp_async16(ring_addr[j] + ((o + 16 * q) ^ swz[j]), cptr[j] + 16 * q);
                 clim[j] += 8;
+                cptr[j] += BLKB;
               }
             }
             cp_async_commit();
