@@ -203,6 +203,10 @@ def port_run(n_sets_sample, G, p, n_threads):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version
+    # banner, for one) goes to stderr instead
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,7 +241,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -523,7 +527,7 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage": stage, "cpu_baseline": cpu_baseline,
             "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local)}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

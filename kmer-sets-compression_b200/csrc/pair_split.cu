@@ -7,7 +7,8 @@
 // is read from HBM once and every output key is written once.
 //
 // split_stream_kernel: one CTA = 256 consecutive finest-level fine buckets of one pair, one thread
-// per fine bucket (about 10 + 10 keys). Units are handed out by a ticket counter.
+// per fine bucket (about 10 + 10 keys). Units are handed out by a ticket counter, chunk-major
+// (chunk c of every pair of the batch before chunk c + 1 of any).
 //   1. the thread merges its two runs straight from global memory (each run is a few sectors that
 //      stay in L1) and remembers which keys are common in two 32-bit masks;
 //   2. a block scan of the per-bucket match counts gives the outputs' finest offsets inside the
@@ -75,8 +76,9 @@ __device__ __forceinline__ void write_levels(uint32_t* __restrict__ base, int N,
 // Units are handed out by a ticket so that a unit only ever waits for units taken earlier.
 template <typename KeyT>
 __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kernel(
-    const SplitPair* __restrict__ pairs, uint32_t chunks_per_pair, uint32_t NF, int N, int F,
+    const SplitPair* __restrict__ pairs, uint32_t n_pairs, uint32_t chunks_per_pair, uint32_t NF, int N, int F,
     unsigned long long* __restrict__ state, uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
+  uint32_t* const watchdog = ticket + 1;
   __shared__ uint32_t s_w[kSpThreads / 32];
   __shared__ uint32_t s_unit;
   __shared__ uint32_t s_g[3];  // exclusive prefix of this chunk inside its pair
@@ -84,7 +86,10 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
   if (tid == 0) s_unit = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t u = s_unit;
-  const uint32_t p = u / chunks_per_pair, c = u - p * chunks_per_pair;
+  // chunk-major order: chunk c of every pair before chunk c + 1 of any. The predecessors of a
+  // unit were taken n_pairs tickets earlier (their totals are long published when it looks back),
+  // and a set shared by several pairs of the batch is read from DRAM once and from L2 after that
+  const uint32_t c = u / n_pairs, p = u - c * n_pairs;
   const SplitPair* P = pairs + p;
   const KeyT* __restrict__ ka = (const KeyT*)P->ka;
   const KeyT* __restrict__ kb = (const KeyT*)P->kb;
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
   const uint32_t preI = before + inc - nI;
   const uint32_t totA = (A1 - A0) - totI, totB = (B1 - B0) - totI;
   // ---- decoupled look-back over the earlier chunks of the pair (warp 0) ---------------------------
-  unsigned long long* const st_me = state + (size_t)u * 4;
+  unsigned long long* const st_me = state + ((size_t)p * chunks_per_pair + c) * 4;
   if (warp == 0) {
     if (lane == 0) {
       st_state(st_me + 0, (1ull << 32) | totI);
@@ -146,8 +151,14 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
       unsigned long long w0 = 0, w1 = 0, w2 = 0;
       if (j >= 0) {
         const unsigned long long* s = state + ((size_t)p * chunks_per_pair + (size_t)j) * 4;
+        uint32_t polls = 0;
         do {
           w0 = ld_state(s); w1 = ld_state(s + 1); w2 = ld_state(s + 2);
+          if (++polls > (1u << 24)) {  // watchdog: a protocol bug must end as KMSC_E_STATE, not as a hung GPU
+            atomicExch(watchdog, 1u);
+            w0 = w1 = w2 = 2ull << 32;
+            break;
+          }
         } while ((w0 >> 32) == 0 || (w1 >> 32) != (w0 >> 32) || (w2 >> 32) != (w0 >> 32));  // 0: not yet; mixed: mid-update
       }
       const bool incl = j >= 0 && (w0 >> 32) == 2;
@@ -267,7 +278,7 @@ static int shell_alloc(kmsc_ctx* ctx, const kmsc_set* like, kmsc_set** out) {
 template <typename KeyT>
 static int launch_split(kmsc_ctx* ctx, const SplitPair* d_pairs, uint32_t total_units, uint32_t cpp, uint32_t NF, int N, int F,
                         unsigned long long* d_state, uint32_t* d_ticket, uint32_t* d_totals) {
-  split_stream_kernel<KeyT><<<total_units, kSpThreads, 0, ctx->stream>>>(d_pairs, cpp, NF, N, F, d_state, d_ticket, d_totals);
+  split_stream_kernel<KeyT><<<total_units, kSpThreads, 0, ctx->stream>>>(d_pairs, total_units / cpp, cpp, NF, N, F, d_state, d_ticket, d_totals);
   count_launch(ctx);
   KMSC_CUDA(cudaGetLastError());
   return KMSC_OK;
@@ -281,8 +292,9 @@ struct SplitOut {           // host bookkeeping of one requested output
 };
 
 // one sub-batch: every pair's staging fits the budget
+// tot_out (may be NULL): m x {|n|, |j\n|, |k\n|}
 static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* const* ks, int32_t m,
-                     const int64_t* hint, kmsc_set** outs[3]) {
+                     const int64_t* hint, kmsc_set** outs[3], uint32_t* tot_out = nullptr) {
   const kmsc_set* like = js[0];
   const int kb = like->key_bytes, N = like->N, F = like->max_level;
   const uint32_t NF = (uint32_t)1 << (N + F);
@@ -354,7 +366,7 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
   uint32_t* d_ticket = (uint32_t*)(base + desc_b + tot_b);
   unsigned long long* d_state = (unsigned long long*)(base + desc_b + tot_b + 256);
   void* pin = nullptr;
-  rc = ctx_pinned(ctx, std::max(desc_b, (size_t)m * 3 * sizeof(CopyDesc)) + tot_b, &pin);
+  rc = ctx_pinned(ctx, std::max(desc_b, (size_t)m * 3 * sizeof(CopyDesc)) + tot_b + 64, &pin);
   if (rc != KMSC_OK) return fail(rc);
   memcpy(pin, hp.data(), (size_t)m * sizeof(SplitPair));
   cudaError_t e = cudaMemcpyAsync(d_pairs, pin, (size_t)m * sizeof(SplitPair), cudaMemcpyHostToDevice, ctx->stream);
@@ -367,10 +379,16 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
   }
   if (rc != KMSC_OK) return fail(rc);
   uint32_t* h_tot = (uint32_t*)((char*)pin + std::max(desc_b, (size_t)m * 3 * sizeof(CopyDesc)));
-  e = cudaMemcpyAsync(h_tot, d_totals, (size_t)m * 3 * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  // totals, then (tot_b bytes later) the ticket word and the watchdog word
+  e = cudaMemcpyAsync(h_tot, d_totals, tot_b + 8, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return fail(cuda_fail(e, "pair_split kernel", __FILE__, __LINE__));
+  if (((const uint32_t*)((const char*)h_tot + tot_b))[1] != 0) {
+    set_error("pair_split: look-back watchdog fired (protocol error)");
+    return fail(KMSC_E_STATE);
+  }
   std::vector<uint32_t> tot(h_tot, h_tot + (size_t)m * 3);
+  if (tot_out) memcpy(tot_out, tot.data(), (size_t)m * 3 * sizeof(uint32_t));
 
   // exact allocations for the staged outputs + one gather copy; pairs whose hint was wrong are redone
   std::vector<CopyDesc> cds;
@@ -482,6 +500,21 @@ int kmsc_pair_split_batch(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_s
     }
     lo = hi;
   }
+  return KMSC_OK;
+}
+
+/* KmerSet::Diff (lib/core/kmer_set.h:191-214): |a \ b| + |b \ a| = the totals of a split without outputs */
+int kmsc_set_diff(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, int64_t* diff) {
+  if (!ctx || !diff || !a || !b) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  if (a->K != b->K || a->N != b->N || a->key_bytes != b->key_bytes) {
+    set_error("sets have different (K,N,KeyType)");
+    return KMSC_E_INVALID;
+  }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  kmsc_set** none[3] = {nullptr, nullptr, nullptr};
+  uint32_t tot[3] = {0, 0, 0};
+  KMSC_TRY(split_run(ctx, &a, &b, 1, nullptr, none, tot));
+  *diff = (int64_t)tot[1] + (int64_t)tot[2];
   return KMSC_OK;
 }
 

@@ -1,18 +1,11 @@
-// set_ops.cu -- P4: set algebra on device CSR sets.
+// set_ops.cu -- P4: unions of device CSR sets.
 //
-// Replaces the split step of KmerSetSet's main loop (reference
-// lib/core/kmer_set_set.h:332-343: n = Intersection(j, k); j.Sub(n); k.Sub(n),
-// built from KmerSet::Sub / Intersection, lib/core/kmer_set.h:177-187, 301-305),
-// KmerSet::Add(other) (:164-174) and KmerSet::Diff (:191-214). The reference
-// decodes two SPSS into hash sets and erases key by key; here both inputs are
-// sorted CSR, so one merge per finest-level fine bucket classifies every key as
-// common / only-in-A / only-in-B. Pass 1 counts per fine bucket, a device scan
-// turns the counts into the outputs' finest-level offsets (which are kept: they
-// ARE the outputs' fine index), pass 2 writes the keys. Inputs must be
-// duplicate-free (true sets).
-//
-// Algorithmic bytes: (n_j + n_k + |n| + |j\n| + |k\n|) * sizeof(Key)
-// + 5 * (2^N + 1) * 4.
+// KmerSet::Add(other) (reference lib/core/kmer_set.h:164-174) over two or more sets -- the union
+// KmerSetSet::Get / KmerSetSetReader::Get build (kmer_set_set.h:433-454, 672-755) -- and the
+// union of two COUNTED sets of the streaming KmerCounter. Both inputs are sorted CSR, so one merge
+// per finest-level fine bucket does it: pass 1 counts per fine bucket, a device scan turns the
+// counts into the output's finest-level offsets (they ARE its fine index), pass 2 writes the keys.
+// (The split n = j & k, j \ n, k \ n and KmerSet::Diff are the single-pass kernel of pair_split.cu.)
 #include "kmsc_common.cuh"
 #include "scan.cuh"
 
@@ -275,17 +268,6 @@ int counted_union(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kms
 using namespace kmsc;
 
 extern "C" {
-
-int kmsc_set_diff(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, int64_t* diff) {
-  if (!ctx || !diff) { set_error("NULL argument"); return KMSC_E_INVALID; }
-  KMSC_TRY(check_pair(a, b));
-  KMSC_CUDA(cudaSetDevice(ctx->device));
-  MergePlan mp;
-  uint32_t tot[3];
-  KMSC_TRY(merge_count(ctx, a, b, &mp, false, tot));
-  *diff = (int64_t)tot[1] + (int64_t)tot[2];
-  return KMSC_OK;
-}
 
 int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_set** out) {
   if (!ctx || !sets || m < 1 || !out) { set_error("bad argument"); return KMSC_E_INVALID; }
