@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stage", action="store_true")
+    ap.add_argument("--no-allreduce", action="store_true", help="diagnostic: time the per-rank partial matrices only")
+    ap.add_argument("--emulate", default="", help="diagnostic, one GPU: R/W = the shard rank R of a W-rank job would hold")
     return ap.parse_args()
 
 
@@ -260,7 +262,10 @@ def main():
     ctx = kmsc.Context(local_rank, stream.cuda_stream)
 
     # data: genome grows with the number of ranks; every rank builds the same sequences
-    Gtot = args.kmers * world + K - 1
+    shard_rank, shard_world = rank, world
+    if args.emulate and world == 1:
+        shard_rank, shard_world = (int(x) for x in args.emulate.split("/"))
+    Gtot = args.kmers * shard_world + K - 1
     seqs = gen_sequences_torch(args.sets, Gtot, args.p, dev)
     str_offs = np.array([0, Gtot], np.int64)
     pinned, nbytes_in = [], 0
@@ -275,13 +280,13 @@ def main():
 
     # prefix shard by cumulative key count of set 0
     lo, hi = 0, 1 << N
-    if world > 1:
+    if shard_world > 1:
         s0 = ctx.set_from_packed(K, N, KB, None, str_offs, words_ptr=pinned[0].data_ptr())
         offs, _ = s0.to_csr()
         s0.free()
-        cuts = [int(np.searchsorted(offs, offs[-1] * r / world)) for r in range(world + 1)]
+        cuts = [int(np.searchsorted(offs, offs[-1] * r / shard_world)) for r in range(shard_world + 1)]
         cuts[0], cuts[-1] = 0, 1 << N
-        lo, hi = cuts[rank], cuts[rank + 1]
+        lo, hi = cuts[shard_rank], cuts[shard_rank + 1]
 
     def build_sets():
         return [ctx.set_from_packed(K, N, KB, None, str_offs, bucket_lo=lo, bucket_hi=hi, words_ptr=h.data_ptr())
@@ -295,7 +300,7 @@ def main():
 
     def step_resident():
         ctx.pair_counts_device(sets, d_out.data_ptr())
-        if world > 1:
+        if world > 1 and not args.no_allreduce:
             dist.all_reduce(d_out)
 
     def barrier():
@@ -325,7 +330,14 @@ def main():
     launches = ctx.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms, float(visits_local)], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own step and kernel time (the line's ms_per_step is the max over ranks)
+        mine = torch.tensor([ms / args.steps, main_ms / max(1, main_launches), float(keys_local)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 4) for x in allr], "kernel_ms": [round(float(x[1]), 4) for x in allr],
+                    "keys": [int(x[2]) for x in allr]}
         tm = t.clone()
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ts = t.clone()
@@ -526,7 +538,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage": stage, "cpu_baseline": cpu_baseline,
-            "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local)}}
+            "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local),
+                      "p3_stats": ctx.pair_counts_stats() if args.no_e2e and args.no_stage else None, "buckets": [int(lo), int(hi)]}}
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -12,8 +12,8 @@
 //
 //   tile     as planned by plan_* (a fine-bucket range holding ~L keys over all sets)
 //   segment  the tile's finest-level range cut into about four pieces per warp (never across a
-//            bucket: keys ascend inside a bucket only), handed out by a counter; the piece of
-//            every set is one contiguous key slice
+//            bucket: keys ascend inside a bucket only; a bucket's pieces follow its share of the
+//            tile's keys), handed out by a counter; the piece of every set is one contiguous slice
 //   ring     per (lane, set) a 16-key window in shared memory, filled by cp.async in 8-key
 //            blocks (global -> shared without registers). Every 4 iterations all lanes top their
 //            rings up in uniform code; the blocks land while the keys before them are merged
@@ -103,6 +103,7 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LY::o_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ uint32_t s_segstart[260];  // first segment of every bucket of the tile (a tile spans <= 256 buckets)
 
   for (int i = tid; i < (SS + 1) * MW; i += T) smask[i] = 0;
   for (int i = tid; i < NS; i += T) {
@@ -203,13 +204,45 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
     const uint32_t X0 = tl.x0 << up, X1 = tl.x1 << up;
     const uint32_t bucket0 = X0 >> finest_level;
     const uint32_t nbk = ((X1 - 1) >> finest_level) - bucket0 + 1;
-    // every bucket part of the tile is cut into P pieces (a power of two) so that there are about
-    // four segments per warp; segments are taken from a counter (buckets differ in size)
-    uint32_t P = 1;
-    while (P * nbk < 4u * NW && P < (1u << finest_level)) P <<= 1;
-    const uint32_t n_seg = nbk * P;
+    // The tile is cut into about four segments per warp, handed out by a counter. One bucket:
+    // P equal pieces. Several buckets: bucket b gets pieces in proportion to its share of the
+    // tile's keys in set 0 (the sets of one job are related, any of them shows where the keys
+    // are) -- a tile may hold one heavy bucket next to many empty ones (the edge of a rank's
+    // prefix range), and a bucket must not be left to a single warp.
+    uint32_t P = 1, n_seg;
     if (tid == 0) misc[kMiscSeg] = 0;
-    __syncthreads();
+    if (nbk == 1) {
+      while (P < 4u * NW && P < (1u << finest_level)) P <<= 1;
+      n_seg = P;
+      __syncthreads();
+    } else {
+      if (warp == 0) {
+        const uint32_t* lv0 = slev[0];
+        const unsigned long long t0 = (unsigned long long)(lv0[X1] - lv0[X0]);
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < nbk; base += 32) {
+          const uint32_t b = base + lane;
+          uint32_t pb = 0;
+          if (b < nbk) {
+            const uint32_t B0 = max(X0, (bucket0 + b) << finest_level), B1 = min(X1, (bucket0 + b + 1) << finest_level);
+            const unsigned long long k = (unsigned long long)(lv0[B1] - lv0[B0]);
+            pb = 1;
+            if (t0 > 0) pb = (uint32_t)min((unsigned long long)(1u << finest_level), max(1ull, (k * 4ull * NW + t0 - 1) / t0));
+          }
+          uint32_t inc = pb;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (b < nbk) s_segstart[b + 1] = carry + inc;
+          carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_segstart[0] = 0;
+      }
+      __syncthreads();
+      n_seg = s_segstart[nbk];
+    }
     auto take_seg = [&]() -> uint32_t {
       uint32_t q = 0;
       if (lane == 0) q = (uint32_t)atomicAdd(&misc[kMiscSeg], 1);
@@ -228,10 +261,20 @@ pair_counts_stream_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw,
       while (!full) {
         if (!have_seg) {
           if (seg_next >= n_seg) break;
-          const uint32_t bk = bucket0 + seg_next / P, piece = seg_next % P;
+          uint32_t bk = bucket0, piece = seg_next, Pb = P;
+          if (nbk > 1) {  // the bucket whose piece range holds this segment
+            uint32_t lo = 0, hi = nbk;
+            while (hi - lo > 1) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (s_segstart[mid] <= seg_next) lo = mid; else hi = mid;
+            }
+            bk = bucket0 + lo;
+            piece = seg_next - s_segstart[lo];
+            Pb = s_segstart[lo + 1] - s_segstart[lo];
+          }
           const uint32_t B0 = max(X0, bk << finest_level), B1 = min(X1, (bk + 1) << finest_level);
-          const uint32_t xa = B0 + (uint32_t)(((unsigned long long)(B1 - B0) * piece) / P);
-          const uint32_t xb = B0 + (uint32_t)(((unsigned long long)(B1 - B0) * (piece + 1)) / P);
+          const uint32_t xa = B0 + (uint32_t)(((unsigned long long)(B1 - B0) * piece) / Pb);
+          const uint32_t xb = B0 + (uint32_t)(((unsigned long long)(B1 - B0) * (piece + 1)) / Pb);
           seg_next = take_seg();
           if (xa >= xb) continue;
           cp_async_wait<0>();  // nothing of the previous segment may still land in the rings
