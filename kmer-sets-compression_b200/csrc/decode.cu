@@ -177,6 +177,7 @@ static int spss_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* t
   PipelineOptions opt{K, N, key_bytes, canonical, bucket_lo, bucket_hi, dedup ? 1 : 0, 1};
   PipelineResult res;
   KMSC_TRY(run_kmer_pipeline(ctx, in, opt, &res));
+  if (res.set && (bucket_lo > 0 || bucket_hi < (1 << N))) { res.set->b_lo = bucket_lo; res.set->b_hi = bucket_hi; }
   *out = res.set;
   return KMSC_OK;
 }

@@ -518,6 +518,7 @@ int kmsc_set_import_range(kmsc_ctx* ctx, int K, int N, int key_bytes, int32_t bu
   int rc = set_build_levels(ctx, s);
   if (rc != KMSC_OK) { kmsc_set_free(ctx, s); return rc; }
   s->has_dups = -1;  // checked on first use by the pair counts
+  s->b_lo = bucket_lo; s->b_hi = bucket_hi;
   *out = s;
   return KMSC_OK;
 }

@@ -79,6 +79,8 @@ struct kmsc_set {
   uint32_t* lev_base = nullptr;  // device, all levels in one allocation
   uint32_t* lev[kmsc::kMaxFineLevel + 1] = {};
   int has_dups = -1;      // -1 unknown, 0 no, 1 yes
+  // buckets outside [b_lo, b_hi) are known to be empty (a rank's prefix shard); -1 = all buckets
+  int32_t b_lo = -1, b_hi = -1;
 };
 
 namespace kmsc {

@@ -1179,7 +1179,17 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
   const int dmax = dmax_for(ns, s0->key_bytes == 8 ? 8 : 4);
   const unsigned long long L_cons = (unsigned long long)(0.75 * dmax);
   const unsigned long long L_max = 1ull << 20;
-  const double mean_bucket = (double)total_keys / (double)nb;  // all sets, per bucket
+  // all sets, per bucket that can hold keys: the sets of a rank's prefix shard have all their
+  // keys in [b_lo, b_hi) (8 shards = 8 x the density the whole bucket space would suggest; the
+  // tile granularity and the table sizing below go by this)
+  int span_lo = nb, span_hi = 0;
+  for (int i = 0; i < n; i++) {
+    const int lo_i = sets[i]->b_lo < 0 ? 0 : sets[i]->b_lo, hi_i = sets[i]->b_hi < 0 ? nb : sets[i]->b_hi;
+    span_lo = std::min(span_lo, lo_i);
+    span_hi = std::max(span_hi, hi_i);
+  }
+  const int nb_live = std::max(1, span_hi - span_lo);
+  const double mean_bucket = (double)total_keys / (double)nb_live;
   unsigned long long st[4] = {0, 0, 0, 0};
 
   // redundancy rho = keys per distinct key inside a tile decides the tile size.

@@ -264,6 +264,7 @@ static int shell_alloc(kmsc_ctx* ctx, const kmsc_set* like, kmsc_set** out) {
   s->max_level = like->max_level;
   s->n_keys = 0;
   s->has_dups = 0;
+  s->b_lo = like->b_lo; s->b_hi = like->b_hi;  // outputs of a rank's shard live in the same bucket range
   cudaError_t e = cudaMallocAsync((void**)&s->lev_base, levels_entries(s->N, s->max_level) * sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMallocAsync levels", __FILE__, __LINE__); }
   uint64_t start = 0;
