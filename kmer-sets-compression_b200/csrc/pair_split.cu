@@ -21,8 +21,9 @@
 // Measured alternatives (profiles/r01_p4_notes.md): a shared-memory tile version (coalesced tile
 // loads, per-key binary search, warp-ballot compaction in place) was 2-3 x slower (4.3-7.2 warp
 // instructions per key against 2.2 here; tools/experiments/pair_split_smem_tile.cu.txt); staging
-// each warp's runs in shared memory with 16-byte loads changed nothing (the kernel waits on the
-// look-back barrier and on instruction issue, not on L1).
+// each warp's runs in shared memory with 16-byte loads changed nothing (not bound by L1); with
+// pair-major unit order a quarter of the time went to the barrier behind the look-back (the
+// predecessors were still merging), chunk-major order took that away (78 -> 52 us per edge).
 //
 // Output sizes are not known before the pass: with a caller-supplied |j & k| (the pair-counts
 // matrix has it) the outputs are allocated exactly and written directly; without it they are
