@@ -73,12 +73,25 @@ __device__ __forceinline__ void write_levels(uint32_t* __restrict__ base, int N,
   }
 }
 
-// One CTA = 256 consecutive finest-level fine buckets of one pair, one thread per fine bucket.
+template <typename KeyT>
+__device__ __forceinline__ uint32_t lower_bound_key(const KeyT* __restrict__ k, uint32_t lo, uint32_t hi, KeyT t) {
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (k[mid] < t) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One CTA = 256 >> qlog consecutive finest-level fine buckets of one pair, 2^qlog threads per
+// fine bucket (qlog = 0 unless the sets are dense: a rank's prefix shard holds N x the keys per
+// fine bucket; the threads of a fine bucket then take the 2^qlog sub-ranges of its key space,
+// found by one binary search each, so that a thread still merges about 10 + 10 keys).
 // Units are handed out by a ticket so that a unit only ever waits for units taken earlier.
 template <typename KeyT>
 __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kernel(
     const SplitPair* __restrict__ pairs, uint32_t n_pairs, uint32_t chunks_per_pair, uint32_t NF, int N, int F,
-    unsigned long long* __restrict__ state, uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
+    int key_bits, int qlog_live, uint32_t xlo, uint32_t xhi, unsigned long long* __restrict__ state,
+    uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
   uint32_t* const watchdog = ticket + 1;
   __shared__ uint32_t s_w[kSpThreads / 32];
   __shared__ uint32_t s_unit;
@@ -96,12 +109,35 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
   const KeyT* __restrict__ kb = (const KeyT*)P->kb;
   const uint32_t* __restrict__ la = P->la;
   const uint32_t* __restrict__ lb = P->lb;
-  const uint32_t x0 = c * kSpThreads, x = x0 + tid;
-  const uint32_t xe = min(x0 + kSpThreads, NF);
+  // fine buckets [xlo, xhi) (multiples of 256) can hold keys: their chunks put 2^qlog_live threads
+  // on a fine bucket; the chunks before and after them (empty for a prefix shard) take 256 each
+  const uint32_t c1 = xlo / kSpThreads, c2 = (xhi - xlo) / ((uint32_t)kSpThreads >> qlog_live);
+  int qlog = 0;
+  uint32_t x0;
+  if (c < c1) x0 = c * kSpThreads;
+  else if (c < c1 + c2) { qlog = qlog_live; x0 = xlo + (c - c1) * ((uint32_t)kSpThreads >> qlog_live); }
+  else x0 = xhi + (c - c1 - c2) * kSpThreads;
+  const uint32_t fpc = (uint32_t)kSpThreads >> qlog;  // fine buckets of this chunk
+  const uint32_t x = x0 + (tid >> qlog), sub = tid & ((1u << qlog) - 1u);
+  const uint32_t xe = min(x0 + fpc, NF);
   const bool live = x < NF;
   // ---- pass 1: merge the two runs, remember which keys are common (runs of <= 32 keys) -----------
   uint32_t i0 = 0, i1 = 0, j0 = 0, j1 = 0;
   if (live) { i0 = la[x]; i1 = la[x + 1]; j0 = lb[x]; j1 = lb[x + 1]; }
+  if (qlog > 0) {
+    // this thread's sub-range of the fine bucket's key space: [t_lo, t_lo + 2^(key_bits - F - qlog))
+    const int sh = key_bits - F - qlog;
+    const unsigned long long t_lo = ((unsigned long long)(x & ((1u << F) - 1u)) << (key_bits - F)) | ((unsigned long long)sub << sh);
+    uint32_t lo_a = i0, lo_b = j0;
+    if (live && sub > 0) {
+      lo_a = lower_bound_key<KeyT>(ka, i0, i1, (KeyT)t_lo);
+      lo_b = lower_bound_key<KeyT>(kb, j0, j1, (KeyT)t_lo);
+    }
+    // the next thread's lower bound is this thread's end (the last sub-range ends with the fine bucket)
+    const uint32_t up_a = __shfl_down_sync(0xffffffffu, lo_a, 1), up_b = __shfl_down_sync(0xffffffffu, lo_b, 1);
+    if (sub + 1 < (1u << qlog)) { i1 = up_a; j1 = up_b; }
+    i0 = lo_a; j0 = lo_b;
+  }
   const uint32_t A0 = la[x0], B0 = lb[x0], A1 = la[xe], B1 = lb[xe];
   const bool small = (i1 - i0 <= 32) && (j1 - j0 <= 32);
   uint32_t mA = 0, mB = 0;  // bit r: key r of the run is common (exact for runs of <= 32 keys)
@@ -204,7 +240,7 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
     uint32_t* const l0 = P->lev[0];
     uint32_t* const l1 = P->lev[1];
     uint32_t* const l2 = P->lev[2];
-    const int tz = x ? min(F, __ffs(x) - 1) : F;  // levels F, F-1, ..., F-tz have an entry at x
+    const int tz = sub ? -1 : x ? min(F, __ffs(x) - 1) : F;  // levels F, F-1, ..., F-tz have an entry at x
     size_t start = ((size_t)1 << N) * (((size_t)1 << F) - 1) + (size_t)F;
     for (int sh = 0; sh <= tz; sh++) {
       const size_t idx = start + (x >> sh);
@@ -279,8 +315,9 @@ static int shell_alloc(kmsc_ctx* ctx, const kmsc_set* like, kmsc_set** out) {
 
 template <typename KeyT>
 static int launch_split(kmsc_ctx* ctx, const SplitPair* d_pairs, uint32_t total_units, uint32_t cpp, uint32_t NF, int N, int F,
-                        unsigned long long* d_state, uint32_t* d_ticket, uint32_t* d_totals) {
-  split_stream_kernel<KeyT><<<total_units, kSpThreads, 0, ctx->stream>>>(d_pairs, total_units / cpp, cpp, NF, N, F, d_state, d_ticket, d_totals);
+                        int key_bits, int qlog, uint32_t xlo, uint32_t xhi, unsigned long long* d_state, uint32_t* d_ticket,
+                        uint32_t* d_totals) {
+  split_stream_kernel<KeyT><<<total_units, kSpThreads, 0, ctx->stream>>>(d_pairs, total_units / cpp, cpp, NF, N, F, key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals);
   count_launch(ctx);
   KMSC_CUDA(cudaGetLastError());
   return KMSC_OK;
@@ -300,7 +337,37 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
   const kmsc_set* like = js[0];
   const int kb = like->key_bytes, N = like->N, F = like->max_level;
   const uint32_t NF = (uint32_t)1 << (N + F);
-  const uint32_t cpp = (NF + kSpThreads - 1) / kSpThreads;
+  // threads per fine bucket: 2^qlog, so that a thread merges about 10 + 10 keys. The density is
+  // taken over the bucket range the sets can hold keys in (a rank's prefix shard is N x denser)
+  int qlog = 0;
+  uint32_t xlo = 0, xhi = NF;  // fine buckets that can hold keys, widened to multiples of 256
+  {
+    double keys = 0;
+    for (int32_t p = 0; p < m; p++) keys += (double)std::max(js[p]->n_keys, ks[p]->n_keys);
+    const int nb = 1 << N;
+    int lo = nb, hi = 0;  // union of the bucket ranges of all sets of the batch
+    for (int32_t p = 0; p < m; p++)
+      for (const kmsc_set* t : {js[p], ks[p]}) {
+        lo = std::min(lo, t->b_lo < 0 ? 0 : (int)t->b_lo);
+        hi = std::max(hi, t->b_hi < 0 ? nb : (int)t->b_hi);
+      }
+    if (hi <= lo) { lo = 0; hi = nb; }
+    const double live_fine = (double)std::max(1, hi - lo) * (double)(1 << F);
+    const double dens = keys / m / live_fine;
+    while (qlog < 5 && qlog < like->key_bits - F && dens > 16.0 * (double)(1 << qlog)) qlog++;
+    if (const char* e = getenv("KMSC_SPLIT_QLOG")) {
+      const int v = atoi(e);
+      if (v >= 0 && v <= 5 && v <= like->key_bits - F) qlog = v;
+    }
+    if (NF >= (uint32_t)kSpThreads) {
+      xlo = ((uint32_t)lo << F) & ~(uint32_t)(kSpThreads - 1);
+      xhi = std::min<uint64_t>(NF, (((uint64_t)hi << F) + kSpThreads - 1) & ~(uint64_t)(kSpThreads - 1));
+    } else {
+      qlog = 0;  // fewer than 256 fine buckets in all: one chunk (of the trailing kind)
+      xlo = xhi = 0;
+    }
+  }
+  const uint32_t cpp = xlo / kSpThreads + (xhi - xlo) / ((uint32_t)kSpThreads >> qlog) + (NF - xhi + kSpThreads - 1) / kSpThreads;
   if ((uint64_t)cpp * m >= 0xffffffffull) { set_error("pair_split_batch: too many work units"); return KMSC_E_INVALID; }
   const uint32_t units = cpp * (uint32_t)m;
 
@@ -375,9 +442,9 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
   if (e == cudaSuccess) e = cudaMemsetAsync(d_totals, 0, tot_b + 256 + state_b, ctx->stream);
   if (e != cudaSuccess) return fail(cuda_fail(e, "pair_split setup", __FILE__, __LINE__));
   switch (kb) {
-    case 2: rc = launch_split<uint16_t>(ctx, d_pairs, units, cpp, NF, N, F, d_state, d_ticket, d_totals); break;
-    case 4: rc = launch_split<uint32_t>(ctx, d_pairs, units, cpp, NF, N, F, d_state, d_ticket, d_totals); break;
-    default: rc = launch_split<unsigned long long>(ctx, d_pairs, units, cpp, NF, N, F, d_state, d_ticket, d_totals); break;
+    case 2: rc = launch_split<uint16_t>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals); break;
+    case 4: rc = launch_split<uint32_t>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals); break;
+    default: rc = launch_split<unsigned long long>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals); break;
   }
   if (rc != KMSC_OK) return fail(rc);
   uint32_t* h_tot = (uint32_t*)((char*)pin + std::max(desc_b, (size_t)m * 3 * sizeof(CopyDesc)));

@@ -185,8 +185,18 @@ def _check_split(ctx, oracle, K, N, pairs_km, hint, want=(True, True, True)):
         assert w[1, 3] == len(pairs_km[0][0]) - n and w[2, 4] == len(pairs_km[0][1]) - n
 
 
+@pytest.fixture(params=["auto", "0", "2", "5"])
+def qlog(request, monkeypatch):
+    """threads per fine bucket of the split kernel (2^qlog): chosen from the density, or forced"""
+    if request.param == "auto":
+        monkeypatch.delenv("KMSC_SPLIT_QLOG", raising=False)
+    else:
+        monkeypatch.setenv("KMSC_SPLIT_QLOG", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("K,N", [(15, 14), (23, 14), (31, 14), (19, 10)])
-def test_pair_split_batch(ctx, oracle, K, N):
+def test_pair_split_batch(ctx, oracle, K, N, qlog):
     """kmsc_pair_split_batch: several pairs per pass, with and without |j & k| hints (right and
     wrong), any subset of outputs; reference semantics kmer_set_set.h:332-343"""
     import synth
@@ -204,7 +214,33 @@ def test_pair_split_batch(ctx, oracle, K, N):
     _check_split(ctx, oracle, K, N, pairs[:3], None, want=(True, False, False))
 
 
-def test_pair_split_dense_runs(ctx, oracle):
+def test_pair_split_on_a_prefix_shard(ctx, oracle, qlog):
+    """sets restricted to a bucket range (one rank's shard of a multi-GPU job): all keys sit in a
+    fraction of the fine buckets, the kernel puts several threads on each"""
+    import synth
+    K, N = 23, 14
+    seqs = synth.phylogeny_sequences(4, 400000, p=0.01, seed=77)
+    lo, hi = 700, 1100
+    dev, kms = [], []
+    for s in seqs:
+        dev.append(ctx.set_from_spss(K, N, 4, [synth.to_ascii(s).decode()], bucket_lo=lo, bucket_hi=hi))
+        km = synth.kmer_set_of(s, K)
+        b = (km >> np.uint64(2 * K - N)).astype(np.int64)
+        kms.append(km[(b >= lo) & (b < hi)])
+    for d, km in zip(dev, kms):
+        assert np.array_equal(d.to_kmers(), km)
+    js, ks = [dev[0], dev[1], dev[3]], [dev[1], dev[2], dev[0]]
+    inter, jm, km_ = ctx.pair_split_batch(js, ks)
+    for p, (a, b) in enumerate([(0, 1), (1, 2), (3, 0)]):
+        wi = oracle.set_intersection(kms[a], kms[b])
+        assert np.array_equal(inter[p].to_kmers(), wi)
+        assert np.array_equal(jm[p].to_kmers(), oracle.set_sub(kms[a], wi))
+        assert np.array_equal(km_[p].to_kmers(), oracle.set_sub(kms[b], wi))
+    w = ctx.pair_counts([inter[0], jm[0], km_[0], dev[0], dev[1]])
+    assert w[0, 1] == 0 and w[0, 3] == len(oracle.set_intersection(kms[0], kms[1])) and w[1, 4] == 0
+
+
+def test_pair_split_dense_runs(ctx, oracle, qlog):
     """keys concentrated in a few fine buckets: chunks that need several rounds, and single fine
     buckets larger than the shared-memory tile (one-thread path)"""
     K, N = 23, 14
