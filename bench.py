@@ -289,8 +289,9 @@ def main():
         lo, hi = cuts[shard_rank], cuts[shard_rank + 1]
 
     def build_sets():
-        return [ctx.set_from_packed(K, N, KB, None, str_offs, bucket_lo=lo, bucket_hi=hi, words_ptr=h.data_ptr())
-                for h in pinned]
+        # one batched launch sequence for all sets (the per-set loop of KmerSetSet's constructor)
+        return ctx.sets_from_packed_batch(K, N, KB, None, [str_offs] * len(pinned), bucket_lo=lo, bucket_hi=hi,
+                                          words_ptrs=[h.data_ptr() for h in pinned])
 
     sets = build_sets()
     n = len(sets)

@@ -114,6 +114,18 @@ int kmsc_set_from_packed(kmsc_ctx* ctx, int K, int N, int key_bytes, const uint6
                          const int64_t* str_offs, int64_t n_strings, int canonical, int dedup,
                          int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
 
+/* The same decode for m sets in ONE batch -- the per-set loop of KmerSetSet's constructor
+ * (lib/core/kmer_set_set.h:138-153: one GetSampledKmerSet task per set). Device work is
+ * batched over the sets (count, partition, sort and offset kernels cover a group of sets per
+ * launch), the host-to-device copies of later groups overlap the kernels of earlier ones,
+ * and the host synchronises twice per group instead of three times per set. words[j] /
+ * str_offs[j] / n_strings[j] as for kmsc_set_from_packed; pinned host memory makes the
+ * copies asynchronous. out: m handles. On error no set is returned. */
+int kmsc_sets_from_packed_batch(kmsc_ctx* ctx, int K, int N, int key_bytes, int32_t m,
+                                const uint64_t* const* words, const int64_t* const* str_offs,
+                                const int64_t* n_strings, int canonical, int dedup,
+                                int32_t bucket_lo, int32_t bucket_hi, kmsc_set** out);
+
 /* SPSS construction support: the de Bruijn neighbours of every k-mer of a set.
  * out (host, 8 * n_keys int32): out[8 i + c] = Kmer::Next(base c) of k-mer i, out[8 i + 4 + c] =
  * Kmer::Prev(base c) (lib/core/kmer.h:136-186), each -1 if absent from the set, else

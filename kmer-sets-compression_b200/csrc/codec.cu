@@ -153,6 +153,20 @@ static int encode_stream(kmsc_ctx* ctx, const uint32_t* d_vals, uint32_t* d_lens
   return KMSC_OK;
 }
 
+// decoded bucket sizes: none may exceed n_keys, and their 64-bit sum is accumulated (the 32-bit
+// scan total alone would accept sizes that only add up modulo 2^32)
+__global__ void check_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t nb, unsigned long long n_keys,
+                                   unsigned long long* __restrict__ total64, int* __restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (i < nb) {
+    v = sizes[i];
+    if (v > n_keys) atomicExch(bad, 1);
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(total64, v);
+}
+
 template <typename T> static void put(uint8_t* p, T v) { memcpy(p, &v, sizeof(T)); }
 template <typename T> static T get(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 
@@ -241,8 +255,14 @@ int kmsc_codec_decode(kmsc_ctx* ctx, const uint8_t* bytes, int64_t n_bytes, kmsc
   }
   const uint32_t nb = (uint32_t)1 << N;
   const uint64_t m_keys = n_keys * wpk;
+  if (m_keys * 4 >= ((uint64_t)1 << 32)) { set_error("bad KMSC header (too many keys for one block)"); return KMSC_E_FORMAT; }  // encode's limit
   const uint64_t n_sctrl = ((uint64_t)nb + 3) / 4, n_kctrl = (m_keys + 3) / 4;
-  if ((uint64_t)n_bytes != kHeader + n_sctrl + n_sdata + n_kctrl + n_kdata) { set_error("KMSC container has the wrong length"); return KMSC_E_FORMAT; }
+  // every length on its own first: the sum below cannot wrap
+  if (n_sdata > (uint64_t)n_bytes || n_kdata > (uint64_t)n_bytes ||
+      (uint64_t)n_bytes != kHeader + n_sctrl + n_sdata + n_kctrl + n_kdata) {
+    set_error("KMSC container has the wrong length");
+    return KMSC_E_FORMAT;
+  }
   KMSC_CUDA(cudaSetDevice(ctx->device));
   kmsc_set* s = nullptr;
   KMSC_TRY(set_alloc(ctx, K, N, key_bytes, (int64_t)n_keys, &s));
@@ -271,15 +291,28 @@ int kmsc_codec_decode(kmsc_ctx* ctx, const uint8_t* bytes, int64_t n_bytes, kmsc
   // bucket sizes -> lev[0]
   const uint8_t* p = d_bytes + kHeader;
   rc = decode_stream(p, p + n_sctrl, nb, n_sdata);
-  if (rc == KMSC_OK) rc = exclusive_scan_u32(ctx, d_vals, s->lev[0], nb, d_scratch + 4, d_scratch + 2);
+  unsigned long long* d_total64 = nullptr;
+  if (rc == KMSC_OK) rc = ctx->small.reserve(64);
+  if (rc == KMSC_OK) {
+    d_total64 = (unsigned long long*)ctx->small.p;
+    e = cudaMemsetAsync(d_total64, 0, 8, ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "codec decode", __FILE__, __LINE__);
+  }
+  if (rc == KMSC_OK) {
+    check_sizes_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(d_vals, nb, n_keys, d_total64, d_bad);
+    count_launch(ctx);
+    rc = exclusive_scan_u32(ctx, d_vals, s->lev[0], nb, d_scratch + 4, d_scratch + 2);
+  }
   p += n_sctrl + n_sdata;
   // the decoded bucket sizes must add up to n_keys before any key is written
   struct { uint32_t total, bad, keys_total, pad; } host;
+  unsigned long long total64 = 0;
   if (rc == KMSC_OK) {
     e = cudaMemcpyAsync(&host, d_scratch, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total64, d_total64, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "codec decode", __FILE__, __LINE__);
-    else if (host.bad || host.keys_total != (uint32_t)n_keys) { set_error("corrupt KMSC container (bucket sizes)"); rc = KMSC_E_FORMAT; }
+    else if (host.bad || total64 != n_keys || host.keys_total != (uint32_t)n_keys) { set_error("corrupt KMSC container (bucket sizes)"); rc = KMSC_E_FORMAT; }
   }
   // key deltas -> keys
   if (rc == KMSC_OK && m_keys > 0) {

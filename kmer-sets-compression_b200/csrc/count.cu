@@ -160,7 +160,8 @@ int filter_t(kmsc_ctx* ctx, const kmsc_set* full, const uint8_t* d_counts, int c
 int count_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, int64_t n, int canonical,
                  int cutoff, int fasta, kmsc_set** out, int64_t* cutoff_count, int64_t* n_distinct) {
   if (!ctx || !out || n < 0 || (n > 0 && !text)) { set_error("bad argument"); return KMSC_E_INVALID; }
-  if (K < 1 || K > 32 || N < 0 || N > 2 * K || 2 * K - N > 8 * key_bytes) { set_error("bad K/N/key_bytes"); return KMSC_E_INVALID; }
+  if (K < 1 || K > 32 || N < 0 || N > 24 || N > 2 * K || 2 * K - N > 8 * key_bytes || 2 * K - N >= 64 ||
+      (key_bytes != 2 && key_bytes != 4 && key_bytes != 8)) { set_error("bad K/N/key_bytes"); return KMSC_E_INVALID; }
   KMSC_CUDA(cudaSetDevice(ctx->device));
   // drop the previous counter
   if (ctx->last_counted_owned && ctx->last_counted) kmsc_set_free(ctx, ctx->last_counted);
@@ -304,7 +305,8 @@ struct kmsc_counter {
 
 int kmsc_counter_create(kmsc_ctx* ctx, int K, int N, int key_bytes, int canonical, kmsc_counter** out) {
   if (!ctx || !out) { set_error("NULL argument"); return KMSC_E_INVALID; }
-  if (K < 1 || K > 32 || N < 0 || N > 2 * K || 2 * K - N > 8 * key_bytes || (key_bytes != 2 && key_bytes != 4 && key_bytes != 8)) {
+  if (K < 1 || K > 32 || N < 0 || N > 24 || N > 2 * K || 2 * K - N > 8 * key_bytes || 2 * K - N >= 64 ||
+      (key_bytes != 2 && key_bytes != 4 && key_bytes != 8)) {
     set_error("bad K/N/key_bytes");
     return KMSC_E_INVALID;
   }

@@ -263,23 +263,35 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
 
   const int threads = 256;
   const unsigned pos_blocks = (unsigned)((in.n_pos + threads - 1) / threads);
-  if (in.n_pos > 0) {
-    hist_kernel<<<pos_blocks, threads, 0, ctx->stream>>>(kp, d_offs);
-    count_launch(ctx);
-  }
-  KMSC_TRY(exclusive_scan_u32(ctx, d_offs, d_offs, NF, d_bsum, d_ctr));
+  // the staged partition sort (partition.cu) covers the usual shapes; the general path below
+  // (global histogram, scatter, per-run sorts) takes what it declines
+  PartPlan plan;
+  KMSC_TRY(partition_plan(ctx, &in, 1, opt, &plan));
+  const bool fast = plan.feasible;
   void* pin = nullptr;
   KMSC_TRY(ctx_pinned(ctx, 64, &pin));
-  KMSC_CUDA(cudaMemcpyAsync(pin, d_ctr, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
-  const int64_t n_occ = *(uint32_t*)pin;
+  int64_t n_occ = 0;
+  if (fast) {
+    n_occ = plan.n_occ[0];
+  } else {
+    if (in.n_pos > 0) {
+      hist_kernel<<<pos_blocks, threads, 0, ctx->stream>>>(kp, d_offs);
+      count_launch(ctx);
+    }
+    KMSC_TRY(exclusive_scan_u32(ctx, d_offs, d_offs, NF, d_bsum, d_ctr));
+    KMSC_CUDA(cudaMemcpyAsync(pin, d_ctr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+    n_occ = *(uint32_t*)pin;
+  }
   res->n_occurrences = n_occ;
 
   kmsc_set* s_all = nullptr;      // mode 0 result; mode 1 result too when no key repeats
   KeyT* d_tmp = nullptr;
   KeyT* d_sorted = nullptr;
-  KMSC_TRY(ctx->work2.reserve((size_t)(n_occ + 8) * sizeof(KeyT)));
-  d_tmp = (KeyT*)ctx->work2.p;
+  if (!fast) {
+    KMSC_TRY(ctx->work2.reserve((size_t)(n_occ + 8) * sizeof(KeyT)));
+    d_tmp = (KeyT*)ctx->work2.p;
+  }
   // dedup (mode 1) sorts straight into the result set: an SPSS spells every k-mer once, so the
   // sorted occurrences normally ARE the set and the run-length pass is skipped
   if (opt.mode == 0 || opt.mode == 1) {
@@ -293,7 +305,23 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
   auto fail = [&](int rc) { if (s_all) kmsc_set_free(ctx, s_all); return rc; };
   bool has_repeats = false, repeats_known = true, levels_done = false;
 
-  if (n_occ > 0) {
+  if (n_occ > 0 && fast) {
+    void* kk = d_sorted;
+    uint32_t* ff = d_offs;
+    int rc_p = partition_run(ctx, &plan, &kk, &ff);
+    if (rc_p != KMSC_OK) return fail(rc_p);
+    if (s_all) {
+      cudaError_t e = cudaMemcpyAsync(s_all->lev[s_all->max_level], d_offs, ent * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline offsets", __FILE__, __LINE__));
+      int rc_l = set_derive_levels(ctx, s_all);
+      if (rc_l != KMSC_OK) return fail(rc_l);
+      levels_done = true;
+    }
+    std::vector<int> rep;
+    rc_p = partition_flags(ctx, &plan, &rep);
+    if (rc_p != KMSC_OK) return fail(rc_p);
+    has_repeats = rep[0] != 0;
+  } else if (n_occ > 0) {
     scatter_kernel<KeyT><<<pos_blocks, threads, 0, ctx->stream>>>(kp, d_offs, d_aux, d_tmp);
     sort_runs_kernel<KeyT><<<(NF + 127) / 128, 128, 0, ctx->stream>>>(d_tmp, d_offs, NF, d_sorted, d_big, d_ctr + 1, d_ctr + 3);
     sort_big_kernel<KeyT><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_tmp, d_offs, d_sorted, d_big, d_ctr + 1,
@@ -401,7 +429,56 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
   return KMSC_OK;
 }
 
+// distinct keys of a set whose buckets are sorted but hold repeats (GetKmerSetFromSPSS's hash-set
+// insert, lib/core/spss.h:1925): run-length pass over every finest fine bucket into a new set
+template <typename KeyT>
+int dedup_t(kmsc_ctx* ctx, const kmsc_set* src, kmsc_set** out) {
+  const int F = src->max_level;
+  const uint32_t NF = (uint32_t)1 << (src->N + F);
+  const size_t ent = (size_t)NF + 1;
+  const size_t sb = scan_scratch_entries(NF);
+  KMSC_TRY(ctx->work.reserve((ent + sb + 64) * 4));
+  uint32_t* d_aux = (uint32_t*)ctx->work.p;
+  uint32_t* d_bsum = d_aux + ent;
+  uint32_t* d_ctr = (uint32_t*)(((uintptr_t)(d_bsum + sb) + 15) & ~(uintptr_t)15);  // [0..1] distinct (u64), [2] kept total
+  KMSC_CUDA(cudaMemsetAsync(d_aux, 0, ent * 4, ctx->stream));
+  KMSC_CUDA(cudaMemsetAsync(d_ctr, 0, 32, ctx->stream));
+  unique_count_kernel<KeyT><<<(NF + 127) / 128, 128, 0, ctx->stream>>>((const KeyT*)src->keys, src->lev[F], NF, 1, d_aux,
+                                                                      (unsigned long long*)d_ctr);
+  count_launch(ctx);
+  KMSC_TRY(exclusive_scan_u32(ctx, d_aux, d_aux, NF, d_bsum, d_ctr + 2));
+  void* pin = nullptr;
+  KMSC_TRY(ctx_pinned(ctx, 64, &pin));
+  KMSC_CUDA(cudaMemcpyAsync(pin, d_ctr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t n_kept = ((const uint32_t*)pin)[2];
+  kmsc_set* s = nullptr;
+  KMSC_TRY(set_alloc(ctx, src->K, src->N, src->key_bytes, n_kept, &s));
+  unique_write_kernel<KeyT><<<(NF + 127) / 128, 128, 0, ctx->stream>>>((const KeyT*)src->keys, src->lev[F], NF, 1, d_aux,
+                                                                      (KeyT*)s->keys, nullptr);
+  count_launch(ctx);
+  cudaError_t e = cudaMemcpyAsync(s->lev[F], d_aux, ent * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+  int rc = e == cudaSuccess ? set_derive_levels(ctx, s) : cuda_fail(e, "dedup offsets", __FILE__, __LINE__);
+  if (rc == KMSC_OK) {
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "dedup finish", __FILE__, __LINE__);
+  }
+  if (rc != KMSC_OK) { kmsc_set_free(ctx, s); return rc; }
+  s->has_dups = 0;
+  s->b_lo = src->b_lo; s->b_hi = src->b_hi;
+  *out = s;
+  return KMSC_OK;
+}
+
 }  // namespace
+
+int dedup_sorted_set(kmsc_ctx* ctx, const kmsc_set* src, kmsc_set** out) {
+  switch (src->key_bytes) {
+    case 2: return dedup_t<uint16_t>(ctx, src, out);
+    case 4: return dedup_t<uint32_t>(ctx, src, out);
+    default: return dedup_t<unsigned long long>(ctx, src, out);
+  }
+}
 
 int run_kmer_pipeline(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& opt, PipelineResult* res) {
   if (in.n_pos >= ((int64_t)1 << 32) - 64) { set_error("input too long for one pass (%lld bases)", (long long)in.n_pos); return KMSC_E_INVALID; }

@@ -30,6 +30,43 @@ struct PipelineResult {
 
 int run_kmer_pipeline(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& opt, PipelineResult* res);
 
+// a new set holding the distinct keys of `src` (buckets sorted, repeats allowed)
+int dedup_sorted_set(kmsc_ctx* ctx, const kmsc_set* src, kmsc_set** out);
+
+// ---- staged partition sort (partition.cu): m jobs in one launch sequence -------------------------
+// plan: count + scan on the device, ONE host synchronisation, then n_occ[j] (k-mer occurrences of
+// job j kept by the bucket filter) is known and the caller allocates the outputs.
+// run: partition + sort, asynchronous; job j's keys (ascending inside every finest-level fine
+// bucket) go to d_keys[j], its finest offset level (2^(N+F)+1 entries) to d_fine[j].
+// flags: one more synchronisation; repeats[j] != 0 if job j holds a k-mer more than once.
+struct PartPlan {
+  bool feasible = false;          // false: shape outside the fast path, use the general pipeline
+  int m = 0;
+  std::vector<int64_t> n_occ;
+  // internal
+  int B1 = 0, R1 = 0, FB = 0, FB2 = 0, tmp_bytes = 0, key_bytes = 0, n_ctas = 0;
+  uint32_t part_max = 0;
+  void* d_jobs = nullptr;
+  void* h_jobs = nullptr;  // pinned host copy of the device job table (ctx->p2tab[slot])
+  PipelineOptions opt{};
+  int64_t max_pos = 0;
+  int slot = 0;
+  bool dedup_in_sort = false;  // set before partition_run: the sort drops repeated keys (then partition_shift)
+  const uint32_t* flags_host = nullptr;  // after partition_flags_async + a stream sync: 4 words per job, [2] = flags
+};
+// slot: which of the context's kP2Slots table sets the plan uses (plans in flight need distinct slots)
+int partition_plan(kmsc_ctx* ctx, const PipelineInput* in, int m, const PipelineOptions& opt, PartPlan* plan, int slot = 0);
+int partition_run(kmsc_ctx* ctx, PartPlan* plan, void* const* d_keys, uint32_t* const* d_fine);
+// queues the read-back of the jobs' flags; valid in plan->flags_host after the stream is synchronised
+int partition_flags_async(kmsc_ctx* ctx, PartPlan* plan);
+int partition_flags(kmsc_ctx* ctx, PartPlan* plan, std::vector<int>* repeats);
+// after a run with dedup_in_sort: jobs[q] (index into the plan) dropped flags_host[4 j + 3] copies;
+// packs old_sets[q] into new_sets[q] (allocated by the caller with the smaller key count)
+int partition_shift(kmsc_ctx* ctx, PartPlan* plan, const std::vector<int>& jobs, kmsc_set* const* old_sets,
+                    kmsc_set* const* new_sets);
+// coarser offset levels of m sets (same K, N) from their finest ones, one launch
+int derive_levels_batch(kmsc_ctx* ctx, kmsc_set* const* sets, int m);
+
 // k-mer starting at base position p of the packed stream (K <= 32)
 __device__ __forceinline__ unsigned long long load_kmer(const unsigned long long* __restrict__ words,
                                                         unsigned long long p, int K) {

@@ -43,6 +43,33 @@ void Scratch::release() {
   cap = 0;
 }
 
+int PinnedTab::acquire(size_t bytes, void** out) {
+  if (pending) { KMSC_CUDA(cudaEventSynchronize(ev)); pending = false; }
+  if (bytes > cap) {
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 2 + 4096;
+    KMSC_CUDA(cudaMallocHost(&p, want));
+    cap = want;
+  }
+  if (!ev) KMSC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  *out = p;
+  return KMSC_OK;
+}
+
+int PinnedTab::commit(cudaStream_t stream) {
+  KMSC_CUDA(cudaEventRecord(ev, stream));
+  pending = true;
+  return KMSC_OK;
+}
+
+void PinnedTab::release() {
+  if (pending && ev) cudaEventSynchronize(ev);
+  if (p) cudaFreeHost(p);
+  if (ev) cudaEventDestroy(ev);
+  p = nullptr; cap = 0; ev = nullptr; pending = false;
+}
+
 int ctx_pinned(kmsc_ctx* ctx, size_t bytes, void** out) {
   if (bytes > ctx->pinned_cap) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -190,6 +217,9 @@ int set_alloc(kmsc_ctx* ctx, int K, int N, int key_bytes, int64_t n_keys, kmsc_s
     return KMSC_E_INVALID;
   }
   if (2 * K - N > 8 * key_bytes) { set_error("2K-N=%d does not fit %d key bytes", 2 * K - N, key_bytes); return KMSC_E_INVALID; }
+  // 64 key bits (K = 32, N = 0) would need 64-bit shifts by 64 in several kernels and has no empty
+  // marker left for the hash tables; none of the reference's instantiations needs it
+  if (2 * K - N >= 64) { set_error("2K-N=%d: keys of 64 bits are not supported (use N >= 1 with K = 32)", 2 * K - N); return KMSC_E_INVALID; }
   if (n_keys < 0 || n_keys >= ((int64_t)1 << 32) - 64) { set_error("n_keys=%lld out of range", (long long)n_keys); return KMSC_E_INVALID; }
   KMSC_CUDA(cudaSetDevice(ctx->device));
   kmsc_set* s = new kmsc_set();
@@ -327,7 +357,14 @@ void kmsc_ctx_destroy(kmsc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ctx->plan.release(); ctx->work.release(); ctx->work2.release(); ctx->work3.release(); ctx->stage.release(); ctx->small.release();
+  ctx->plan.release(); ctx->work.release(); ctx->work2.release(); ctx->work3.release(); ctx->stage.release(); ctx->small.release(); for (int i = 0; i < kmsc_ctx::kP2Slots; i++) {
+    ctx->p2a[i].release(); ctx->p2b[i].release(); ctx->p2tab[i].release(); ctx->p2rb[i].release();
+    if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+  }
+  for (auto& t : ctx->tabs_dev) t.release();
+  for (auto& t : ctx->tab) t.release();
+  if (ctx->fence_ev) cudaEventDestroy(ctx->fence_ev);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 3; i++)
     if (ctx->pc_ev[i]) cudaEventDestroy(ctx->pc_ev[i]);
@@ -349,12 +386,33 @@ int64_t kmsc_ctx_launch_count(kmsc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int kmsc_set_from_csr(kmsc_ctx* ctx, int K, int N, int key_bytes, const int64_t* offs,
                       const void* keys, kmsc_set** out) {
   if (!ctx || !offs || !out) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  // the shape first: offs has 2^N + 1 entries only if N is sane
+  if (K < 1 || K > 32 || N < 0 || N > 24 || N > 2 * K || (key_bytes != 2 && key_bytes != 4 && key_bytes != 8) ||
+      2 * K - N > 8 * key_bytes || 2 * K - N >= 64) {
+    set_error("bad K=%d N=%d key_bytes=%d", K, N, key_bytes);
+    return KMSC_E_INVALID;
+  }
   const int64_t nb = (int64_t)1 << N;
   if (offs[0] != 0) { set_error("offs[0] must be 0"); return KMSC_E_INVALID; }
   for (int64_t b = 0; b < nb; b++)
     if (offs[b + 1] < offs[b]) { set_error("offs not monotone at bucket %lld", (long long)b); return KMSC_E_INVALID; }
   const int64_t n = offs[nb];
   if (n > 0 && !keys) { set_error("keys is NULL"); return KMSC_E_INVALID; }
+  {
+    // every consumer (offset levels, merges, tiles) assumes keys ascending inside each bucket and
+    // below 2^(2K-N): refuse anything else here rather than return wrong matrices later
+    const int key_bits = 2 * K - N;
+    const uint64_t lim = key_bits >= 64 ? ~0ull : (((uint64_t)1 << key_bits) - 1);
+    for (int64_t b = 0; b < nb; b++) {
+      uint64_t prev = 0;
+      for (int64_t i = offs[b]; i < offs[b + 1]; i++) {
+        const uint64_t k = key_bytes == 2 ? ((const uint16_t*)keys)[i] : key_bytes == 4 ? ((const uint32_t*)keys)[i] : ((const uint64_t*)keys)[i];
+        if (k > lim) { set_error("key %lld exceeds %d bits", (long long)i, key_bits); return KMSC_E_INVALID; }
+        if (i > offs[b] && k < prev) { set_error("keys not ascending in bucket %lld", (long long)b); return KMSC_E_INVALID; }
+        prev = k;
+      }
+    }
+  }
   kmsc_set* s = nullptr;
   KMSC_TRY(set_alloc(ctx, K, N, key_bytes, n, &s));
   // stage offs as uint32 through pinned memory

@@ -35,6 +35,18 @@ struct Scratch {
   void release();
 };
 
+// pinned host table that is copied to the device asynchronously: acquire() waits until the
+// previous copy out of it has run, commit() marks the new one
+struct PinnedTab {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+  int acquire(size_t bytes, void** out);
+  int commit(cudaStream_t stream);
+  void release();
+};
+
 }  // namespace kmsc
 
 struct kmsc_ctx {
@@ -49,6 +61,17 @@ struct kmsc_ctx {
   kmsc::Scratch work3;
   kmsc::Scratch stage;    // input staging (text, packed bases)
   kmsc::Scratch small;    // small per-call device arrays (descriptors, ids)
+  // staged partition sort: up to kP2Slots groups of jobs in flight, each with its own tables
+  static constexpr int kP2Slots = 4;
+  kmsc::Scratch p2a[kP2Slots];      // job table, bin bases, cursors
+  kmsc::Scratch p2b[kP2Slots];      // first-level output
+  kmsc::PinnedTab p2tab[kP2Slots];  // host side of the job table
+  kmsc::PinnedTab p2rb[kP2Slots];   // read-backs (n_occ, largest partition, repeat flags)
+  kmsc::Scratch tabs_dev[2];        // device copies of small host tables (0 level jobs, 1 tail jobs)
+  kmsc::PinnedTab tab[2];           // their host side
+  cudaStream_t copy_stream = nullptr;  // host-to-device copies of a batch decode
+  cudaEvent_t copy_ev[kP2Slots] = {};  // "group g is on the device"
+  cudaEvent_t fence_ev = nullptr;
   void* pinned = nullptr; // pinned host staging
   size_t pinned_cap = 0;
   // pair_counts: redundancy (keys per distinct key in a tile) seen by the last call

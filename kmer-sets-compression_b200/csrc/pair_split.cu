@@ -541,6 +541,12 @@ int kmsc_pair_split_batch(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_s
     }
   }
   KMSC_CUDA(cudaSetDevice(ctx->device));
+  // the merge assumes true sets: a repeated key would survive in j \ n while also being in n
+  for (int32_t p = 0; p < m; p++)
+    for (const kmsc_set* x : {js[p], ks[p]}) {
+      KMSC_TRY(set_check_dups(ctx, const_cast<kmsc_set*>(x)));
+      if (x->has_dups == 1) { set_error("pair %d: a set holds duplicate keys (split / diff need true sets)", p); return KMSC_E_INVALID; }
+    }
   kmsc_set** outs[3] = {inter, j_minus, k_minus};
   for (int q = 0; q < 3; q++)
     if (outs[q]) for (int32_t p = 0; p < m; p++) outs[q][p] = nullptr;
@@ -580,6 +586,10 @@ int kmsc_set_diff(kmsc_ctx* ctx, const kmsc_set* a, const kmsc_set* b, int64_t* 
     return KMSC_E_INVALID;
   }
   KMSC_CUDA(cudaSetDevice(ctx->device));
+  for (const kmsc_set* x : {a, b}) {
+    KMSC_TRY(set_check_dups(ctx, const_cast<kmsc_set*>(x)));
+    if (x->has_dups == 1) { set_error("a set holds duplicate keys (split / diff need true sets)"); return KMSC_E_INVALID; }
+  }
   kmsc_set** none[3] = {nullptr, nullptr, nullptr};
   uint32_t tot[3] = {0, 0, 0};
   KMSC_TRY(split_run(ctx, &a, &b, 1, nullptr, none, tot));

@@ -272,6 +272,11 @@ extern "C" {
 int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_set** out) {
   if (!ctx || !sets || m < 1 || !out) { set_error("bad argument"); return KMSC_E_INVALID; }
   KMSC_CUDA(cudaSetDevice(ctx->device));
+  for (int32_t t = 0; t < m; t++) {
+    if (!sets[t]) { set_error("sets[%d] is NULL", t); return KMSC_E_INVALID; }
+    KMSC_TRY(set_check_dups(ctx, const_cast<kmsc_set*>(sets[t])));
+    if (sets[t]->has_dups == 1) { set_error("sets[%d] holds duplicate keys (union needs true sets)", t); return KMSC_E_INVALID; }
+  }
   // left fold of two-way unions; intermediates are freed as we go
   kmsc_set* acc = nullptr;
   for (int32_t t = 0; t < m; t++) {

@@ -89,7 +89,9 @@ class KmerSetCompact {
     std::vector<std::string> out(static_cast<std::size_t>(n_));
     std::int64_t pos = 0;
     for (std::int64_t i = 0; i < n_; i++) {
-      const std::int64_t len = static_cast<std::int64_t>(lens[static_cast<std::size_t>(i)]) + K;
+      // a string shorter than K is stored as (length - K) mod 2^32 and comes back by the same
+      // 32-bit arithmetic (the reference's GetLengths, lib/core/kmer_set_compact.h:269-287)
+      const std::int64_t len = static_cast<std::uint32_t>(lens[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(K));
       std::string& s = out[static_cast<std::size_t>(i)];
       s.resize(static_cast<std::size_t>(len));
       for (std::int64_t j = 0; j < len; j++, pos++)
@@ -104,7 +106,7 @@ class KmerSetCompact {
     std::vector<std::uint32_t> lengths(spss.size());
     std::int64_t total = 0;
     for (std::size_t i = 0; i < spss.size(); i++) {
-      lengths[i] = static_cast<std::uint32_t>(spss[i].size()) - K;
+      lengths[i] = static_cast<std::uint32_t>(spss[i].size()) - static_cast<std::uint32_t>(K);  // mod 2^32 for short lines, as the reference
       total += static_cast<std::int64_t>(spss[i].size());
     }
     n_bases_ = total;
@@ -122,7 +124,8 @@ class KmerSetCompact {
     const std::vector<std::uint32_t> lens = Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_));
     std::vector<std::int64_t> offs(static_cast<std::size_t>(n_) + 1, 0);
     for (std::int64_t i = 0; i < n_; i++)
-      offs[static_cast<std::size_t>(i) + 1] = offs[static_cast<std::size_t>(i)] + lens[static_cast<std::size_t>(i)] + K;
+      offs[static_cast<std::size_t>(i) + 1] =
+          offs[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(lens[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(K));
     kmsc_set* s = nullptr;
     std::lock_guard<std::mutex> l(Device::Mu());
     Device::Check(kmsc_set_from_packed(Device::Ctx(), K, N, static_cast<int>(sizeof(KeyType)), words_.data(), offs.data(), n_,

@@ -113,6 +113,8 @@ class KmerSetSet {
     for (const Compact& c : kmer_sets_compact_) sets.push_back(c.ToKmerSet(canonical, n_workers));
 
     std::vector<std::int64_t> W = PairCounts(sets, opt.exact ? nullptr : &ids);  // dense n x n
+    initial_weights_ = W;
+    bucket_ids_ = bucket_ids;
     int n = n0;
     merges_.clear();
 
@@ -240,6 +242,9 @@ class KmerSetSet {
   // (j, k, weight) of every merge, in order: the observable the reference only logs (:324)
   const std::vector<std::tuple<int, int, std::int64_t>>& Merges() const { return merges_; }
   const internal::AdjacencyList& Children() const { return children_; }
+  // the initial n0 x n0 weight matrix (reference :187-219) and the bucket sample it was taken over
+  const std::vector<std::int64_t>& InitialWeights() const { return initial_weights_; }
+  const std::vector<int>& BucketIds() const { return bucket_ids_; }
 
   // ---- device helpers shared with the mst driver -------------------------------------------
   static std::vector<std::int64_t> PairCounts(const std::vector<Set>& sets, const std::vector<std::int32_t>* ids) {
@@ -283,6 +288,8 @@ class KmerSetSet {
   internal::AdjacencyList children_;
   std::vector<Compact> kmer_sets_compact_;
   std::vector<std::tuple<int, int, std::int64_t>> merges_;
+  std::vector<std::int64_t> initial_weights_;
+  std::vector<int> bucket_ids_;
 };
 
 // Lazy reader over a dumped directory (reference :622-775)
@@ -406,6 +413,99 @@ MstResult<K, N, KeyType> BuildMst(const std::vector<KmerSet<K, N, KeyType>>& set
   if (!r.edges.empty()) Set::SplitBatch(js, ks, inter_sizes, nullptr, &r.del, &r.add);
   return r;
 }
+
+// ---- on-disk form of an mst result (no counterpart in the reference; text like its formats) ----
+// meta.<ext>: line 1 "mst <n>", then one line "<parent> <child> <distance>" per tree edge in
+// BuildMst order; 0.<ext> = SPSS of the root set; <child>.add.<ext> / <child>.del.<ext> = SPSS of
+// S_child \ S_parent and S_parent \ S_child.
+template <int K, int N, typename KeyType>
+Status DumpMst(const MstResult<K, N, KeyType>& r, const KmerSetCompact<K, N, KeyType>& root, int n_sets,
+               const std::string& directory_name, const std::string& compressor, const std::string& extension,
+               bool canonical, int n_workers) {
+  using Compact = KmerSetCompact<K, N, KeyType>;
+  try {
+    std::filesystem::create_directories(directory_name);
+  } catch (...) {
+    return InternalError("failed to create a directory");
+  }
+  const std::filesystem::path dir(directory_name);
+  std::vector<std::string> meta;
+  meta.push_back("mst " + std::to_string(n_sets));
+  for (const MstEdge& e : r.edges)
+    meta.push_back(std::to_string(e.parent) + " " + std::to_string(e.child) + " " + std::to_string(e.distance));
+  Status st = WriteLines((dir / ("meta." + extension)).string(), compressor, meta);
+  if (!st.ok()) return st;
+  st = root.Dump((dir / ("0." + extension)).string(), compressor, n_workers);
+  if (!st.ok()) return st;
+  int fail_count = 0;
+  for (std::size_t i = 0; i < r.edges.size(); i++) {
+    const std::string c = std::to_string(r.edges[i].child);
+    if (!Compact::FromKmerSet(r.add[i], canonical, true, n_workers).Dump((dir / (c + ".add." + extension)).string(), compressor, n_workers).ok()) fail_count++;
+    if (!Compact::FromKmerSet(r.del[i], canonical, true, n_workers).Dump((dir / (c + ".del." + extension)).string(), compressor, n_workers).ok()) fail_count++;
+  }
+  if (fail_count > 0) return InternalError("failed to write " + std::to_string(fail_count) + " files");
+  return OkStatus();
+}
+
+template <int K, int N, typename KeyType>
+class MstReader {
+ public:
+  static bool IsMstDirectory(const std::string& directory_name, const std::string& extension, const std::string& decompressor) {
+    StatusOr<std::vector<std::string>> v = ReadLines((std::filesystem::path(directory_name) / ("meta." + extension)).string(), decompressor);
+    return v.ok() && !v.value().empty() && v.value()[0].rfind("mst ", 0) == 0;
+  }
+  static StatusOr<MstReader> FromDirectory(std::string directory_name, std::string extension, std::string decompressor,
+                                           bool canonical) {
+    StatusOr<std::vector<std::string>> v = ReadLines((std::filesystem::path(directory_name) / ("meta." + extension)).string(), decompressor);
+    if (!v.ok()) return v.status();
+    if (v.value().empty() || v.value()[0].rfind("mst ", 0) != 0) return InternalError("malformed meta file");
+    MstReader r;
+    r.size_ = std::atoi(v.value()[0].c_str() + 4);
+    r.parent_.assign(static_cast<std::size_t>(r.size_), -1);
+    for (std::size_t i = 1; i < v.value().size(); i++) {
+      std::stringstream ss(v.value()[i]);
+      int p = -1, c = -1;
+      std::int64_t d = 0;
+      if (!(ss >> p >> c >> d)) continue;
+      if (c < 0 || c >= r.size_ || p < 0 || p >= r.size_) return InternalError("malformed meta file");
+      r.parent_[static_cast<std::size_t>(c)] = p;
+    }
+    r.directory_name_ = std::move(directory_name);
+    r.extension_ = std::move(extension);
+    r.decompressor_ = std::move(decompressor);
+    r.canonical_ = canonical;
+    return r;
+  }
+  int Size() const { return size_; }
+  // S_i = ((S_root \ del) | add) applied along the tree path from the root to i
+  StatusOr<KmerSet<K, N, KeyType>> Get(int i, int n_workers) const {
+    using Compact = KmerSetCompact<K, N, KeyType>;
+    std::vector<int> path;
+    for (int c = i; c != 0; c = parent_[static_cast<std::size_t>(c)]) {
+      if (c < 0 || path.size() > parent_.size()) return InternalError("malformed tree");
+      path.push_back(c);
+    }
+    const std::filesystem::path dir(directory_name_);
+    StatusOr<Compact> root = Compact::Load((dir / ("0." + extension_)).string(), decompressor_);
+    if (!root.ok()) return root.status();
+    KmerSet<K, N, KeyType> s = root.value().ToKmerSet(canonical_, n_workers);
+    for (auto it = path.rbegin(); it != path.rend(); ++it) {
+      const std::string c = std::to_string(*it);
+      StatusOr<Compact> add = Compact::Load((dir / (c + ".add." + extension_)).string(), decompressor_);
+      StatusOr<Compact> del = Compact::Load((dir / (c + ".del." + extension_)).string(), decompressor_);
+      if (!add.ok() || !del.ok()) return InternalError("failed to load data from 1 files");
+      s.Sub(del.value().ToKmerSet(canonical_, n_workers), n_workers);
+      s.Add(add.value().ToKmerSet(canonical_, n_workers), n_workers);
+    }
+    return s;
+  }
+
+ private:
+  std::string directory_name_, extension_, decompressor_;
+  bool canonical_ = false;
+  int size_ = 0;
+  std::vector<int> parent_;
+};
 
 }  // namespace kmsc
 #endif

@@ -2,8 +2,14 @@
 // (src/kmerset-multiple-compress.cc:33-163): same flags (--k --workers --canonical
 // --decompressor --compressor --out --extension --out_graph), same input (one SPSS text
 // file per set) and the same output directory format (meta.<ext> + <i>.<ext>, DOT graph).
-// Extra flags: --exact (all-bucket weights instead of the 2% sample), --seed (bucket sample).
+// Extra flags: --exact (all-bucket weights instead of the 2% sample), --seed (bucket sample),
+// --bucket_ids_file (explicit sample, one id per line: replays a seeded reference run),
+// --max_iterations, --driver=greedy|mst (mst: Kruskal over the exact symmetric-difference
+// matrix + one difference-set pair per tree edge; its own directory layout, see DumpMst),
+// --trace=<file> (weight matrix, merges / tree edges with the sizes and XOR hashes of the
+// difference sets: what the parity tests compare with the oracle).
 #include <cstdio>
+#include <fstream>
 #include <string>
 #include <vector>
 
@@ -29,18 +35,58 @@ int Main(const Flags& flags) {
   }
   for (std::size_t i = 0; i < sets.size(); i++)
     Info("i = " + std::to_string(i) + ", size = " + std::to_string(sets[i].Size(n_workers)));
+  const std::string trace = flags.Str("trace", "");
+  const std::string out = flags.Str("out", "");
+  if (flags.Str("driver", "greedy") == "mst") {
+    Info("constructing the spanning tree");
+    std::vector<KmerSet<K, N, KeyType>> ksets;
+    for (const auto& c : sets) ksets.push_back(c.ToKmerSet(canonical, n_workers));
+    const MstResult<K, N, KeyType> r = BuildMst<K, N, KeyType>(ksets);
+    Info("constructed the spanning tree, edges = " + std::to_string(r.edges.size()));
+    if (!trace.empty()) {
+      std::ofstream t(trace);
+      const std::size_t n = sets.size();
+      t << "driver mst\nn " << n << "\nW";
+      for (std::int64_t w : r.W) t << ' ' << w;
+      t << "\n";
+      for (std::size_t i = 0; i < r.edges.size(); i++)
+        t << "edge " << r.edges[i].parent << ' ' << r.edges[i].child << ' ' << r.edges[i].distance << ' '
+          << r.add[i].Size() << ' ' << r.add[i].Hash(n_workers) << ' ' << r.del[i].Size() << ' ' << r.del[i].Hash(n_workers) << "\n";
+    }
+    if (!out.empty() && !sets.empty()) {
+      Status st = DumpMst<K, N, KeyType>(r, sets[0], static_cast<int>(sets.size()), out, flags.Str("compressor", ""),
+                                         flags.Str("extension", "txt"), canonical, n_workers);
+      if (!st.ok()) { Error("failed to dump the spanning tree: " + st.ToString()); return 1; }
+    }
+    return 0;
+  }
   Info("constructing kmer_set_set");
   KmerSetSetOptions opt;
   opt.exact = flags.Bool("exact", false);
   opt.seed = static_cast<std::uint64_t>(flags.Int("seed", 0));
+  opt.max_iterations = flags.Int("max_iterations", -1);
+  const std::string ids_file = flags.Str("bucket_ids_file", "");
+  if (!ids_file.empty()) {
+    std::ifstream f(ids_file);
+    int id;
+    while (f >> id) opt.bucket_ids.push_back(id);
+    if (opt.bucket_ids.empty()) { Error("no bucket ids in " + ids_file); return 1; }
+  }
+  const std::size_t n0 = sets.size();
   KmerSetSet<K, N, KeyType> kss(std::move(sets), canonical, n_workers, opt);
   Info("constructed kmer_set_set, size = " + std::to_string(kss.Size()));
+  if (!trace.empty()) {
+    std::ofstream t(trace);
+    t << "driver greedy\nn " << n0 << "\nW";
+    for (std::int64_t w : kss.InitialWeights()) t << ' ' << w;
+    t << "\n";
+    for (const auto& m : kss.Merges()) t << "merge " << std::get<0>(m) << ' ' << std::get<1>(m) << ' ' << std::get<2>(m) << "\n";
+  }
   const std::string out_graph = flags.Str("out_graph", "");
   if (!out_graph.empty()) {
     Status st = kss.DumpGraph(out_graph);
     if (!st.ok()) { Error("failed to dump graph: " + st.ToString()); return 1; }
   }
-  const std::string out = flags.Str("out", "");
   if (!out.empty()) {
     Status st = kss.Dump(out, flags.Str("compressor", ""), flags.Str("extension", "txt"), n_workers);
     if (!st.ok()) { Error("failed to dump kmer_set_set: " + st.ToString()); return 1; }

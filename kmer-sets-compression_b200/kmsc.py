@@ -30,7 +30,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
@@ -83,6 +83,9 @@ def lib() -> C.CDLL:
                                      C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
     L.kmsc_set_from_packed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, _i64p, C.c_int64,
                                        C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.kmsc_sets_from_packed_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), _i64p, C.c_int, C.c_int, C.c_int32, C.c_int32,
+                                              C.POINTER(C.c_void_p)]
     L.kmsc_pair_counts_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.kmsc_pair_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i64p, _i64p]
     L.kmsc_pair_counts_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, C.c_void_p]
@@ -235,6 +238,24 @@ class Context:
         _check(lib().kmsc_set_from_packed(self.h, K, N, key_bytes, C.c_void_p(words_ptr), str_offs.ctypes.data_as(_i64p),
                                           len(str_offs) - 1, int(canonical), int(dedup), bucket_lo, hi, C.byref(h)))
         return DeviceSet(self, h.value)
+
+    def sets_from_packed_batch(self, K, N, key_bytes, words_list, str_offs_list, canonical=True, dedup=True,
+                               bucket_lo=0, bucket_hi=None, words_ptrs=None):
+        """m packed SPSS -> m device sets in one batched launch sequence (KmerSetSet ctor's per-set loop);
+        words_ptrs: raw host pointers (e.g. pinned torch tensors) instead of arrays"""
+        m = len(str_offs_list)
+        offs = [np.ascontiguousarray(o, np.int64) for o in str_offs_list]
+        if words_ptrs is None:
+            words_list = [np.ascontiguousarray(w, np.uint64) for w in words_list]
+            words_ptrs = [w.ctypes.data for w in words_list]
+        wp = (C.c_void_p * m)(*words_ptrs)
+        op = (C.c_void_p * m)(*[o.ctypes.data for o in offs])
+        ns = np.array([len(o) - 1 for o in offs], np.int64)
+        out = (C.c_void_p * m)()
+        hi = (1 << N) if bucket_hi is None else bucket_hi
+        _check(lib().kmsc_sets_from_packed_batch(self.h, K, N, key_bytes, m, wp, op, ns.ctypes.data_as(_i64p), int(canonical),
+                                                 int(dedup), bucket_lo, hi, out))
+        return [DeviceSet(self, out[j]) for j in range(m)]
 
     def pair_counts_stats(self) -> dict:
         out = (C.c_double * 8)()

@@ -661,6 +661,70 @@ void kmsc_o_dsu_unite(kmsc_o_dsu* d, int32_t x, int32_t y) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* `mst` driver (north_star variant; the snapshot has no counterpart) */
+/* ------------------------------------------------------------------------- */
+
+typedef struct { int64_t d; int32_t i, j; } mst_cand;
+
+static int mst_cand_cmp(const void* a, const void* b) {
+  const mst_cand* x = (const mst_cand*)a;
+  const mst_cand* y = (const mst_cand*)b;
+  if (x->d != y->d) return x->d < y->d ? -1 : 1;
+  if (x->i != y->i) return x->i < y->i ? -1 : 1;
+  if (x->j != y->j) return x->j < y->j ? -1 : 1;
+  return 0;
+}
+
+/* w: exact n x n intersection matrix (diagonal = set sizes, upper triangle read).
+ * d(i,j) = |S_i| + |S_j| - 2 w[i][j]; candidate edges in (d, i, j) ascending order; Kruskal
+ * with the union-find of lib/core/parallel_disjoint_set.h:53-78, 98-106 (above); the tree is
+ * oriented by a breadth-first walk from node 0 that visits a node's neighbours in ascending
+ * index order. Output: n - 1 rows (parent, child) in visiting order and their distances.
+ * Returns the number of edges (n - 1, or less if some d is unreachable: never for n >= 1). */
+int32_t kmsc_o_mst(const int64_t* w, int32_t n, int32_t* edges, int64_t* dist) {
+  if (n <= 1) return 0;
+  const size_t nc = (size_t)n * (size_t)(n - 1) / 2;
+  mst_cand* c = (mst_cand*)malloc(nc * sizeof(mst_cand));
+  size_t t = 0;
+  for (int32_t i = 0; i < n; i++)
+    for (int32_t j = i + 1; j < n; j++) {
+      c[t].d = w[(size_t)i * n + i] + w[(size_t)j * n + j] - 2 * w[(size_t)i * n + j];
+      c[t].i = i; c[t].j = j; t++;
+    }
+  qsort(c, nc, sizeof(mst_cand), mst_cand_cmp);
+  kmsc_o_dsu* dsu = kmsc_o_dsu_new(n);
+  /* adjacency of the tree as an n x n distance table (-1 = no edge): n is small (sets) */
+  int64_t* adj = (int64_t*)malloc((size_t)n * n * sizeof(int64_t));
+  for (size_t q = 0; q < (size_t)n * n; q++) adj[q] = -1;
+  int32_t taken = 0;
+  for (size_t q = 0; q < nc && taken < n - 1; q++) {
+    if (kmsc_o_dsu_same(dsu, c[q].i, c[q].j)) continue;
+    kmsc_o_dsu_unite(dsu, c[q].i, c[q].j);
+    adj[(size_t)c[q].i * n + c[q].j] = c[q].d;
+    adj[(size_t)c[q].j * n + c[q].i] = c[q].d;
+    taken++;
+  }
+  int32_t* queue = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+  char* seen = (char*)calloc((size_t)n, 1);
+  int32_t head = 0, tail = 0, ne = 0;
+  queue[tail++] = 0; seen[0] = 1;
+  while (head < tail) {
+    const int32_t p = queue[head++];
+    for (int32_t x = 0; x < n; x++) {
+      if (adj[(size_t)p * n + x] < 0 || seen[x]) continue;
+      seen[x] = 1;
+      edges[2 * ne] = p; edges[2 * ne + 1] = x;
+      dist[ne] = adj[(size_t)p * n + x];
+      ne++;
+      queue[tail++] = x;
+    }
+  }
+  free(queue); free(seen); free(adj); free(c);
+  kmsc_o_dsu_free(dsu);
+  return ne;
+}
+
+/* ------------------------------------------------------------------------- */
 /* streamvbyte "0124" (lemire/streamvbyte v0.4.1, published format)           */
 /* ------------------------------------------------------------------------- */
 

@@ -128,6 +128,13 @@ int32_t  kmsc_o_dsu_find(kmsc_o_dsu*, int32_t x);            /* :24-40 */
 int      kmsc_o_dsu_same(kmsc_o_dsu*, int32_t x, int32_t y); /* :43-50 */
 void     kmsc_o_dsu_unite(kmsc_o_dsu*, int32_t x, int32_t y);/* :53-78 */
 
+/* ---- `mst` driver (north_star; no counterpart in the snapshot: SURVEY.md App. C) ---------- */
+/* w = exact n x n intersection matrix with the set sizes on the diagonal. Kruskal over
+ * d(i,j) = |S_i| + |S_j| - 2 w[i][j], candidates ordered by (d, i, j), union-find as
+ * parallel_disjoint_set.h:53-78; tree oriented breadth-first from node 0, neighbours in
+ * ascending index order. edges: (parent, child) x (n-1); dist: n-1. Returns the edge count. */
+int32_t  kmsc_o_mst(const int64_t* w, int32_t n, int32_t* edges, int64_t* dist);
+
 /* ---- streamvbyte "0124" (third party, v0.4.1; published format) ------------ */
 size_t   kmsc_o_svb0124_max_bytes(uint32_t n);
 size_t   kmsc_o_svb0124_encode(const uint32_t* in, uint32_t n, uint8_t* out);

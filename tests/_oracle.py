@@ -103,6 +103,8 @@ class Oracle:
         L.kmsc_o_greedy_should_stop.argtypes = [C.c_int64, C.c_int64, C.c_int32]
         L.kmsc_o_greedy_argmax.argtypes = [i64p, C.c_int32, i32p, i32p]
         L.kmsc_o_greedy_argmax.restype = C.c_int64
+        L.kmsc_o_mst.argtypes = [i64p, C.c_int32, i32p, i64p]
+        L.kmsc_o_mst.restype = C.c_int32
         L.kmsc_o_dsu_new.argtypes = [C.c_int32]
         L.kmsc_o_dsu_new.restype = C.c_void_p
         L.kmsc_o_dsu_free.argtypes = [C.c_void_p]
@@ -284,6 +286,15 @@ class Oracle:
         j, k = C.c_int32(), C.c_int32()
         v = self.lib.kmsc_o_greedy_argmax(_ptr(w, i64p), w.shape[0], C.byref(j), C.byref(k))
         return v, j.value, k.value
+
+    def mst(self, w):
+        """(edges [(parent, child)], distances) of the `mst` driver over an exact intersection matrix"""
+        w = np.ascontiguousarray(w, np.int64)
+        n = w.shape[0]
+        edges = np.zeros((max(1, n - 1), 2), np.int32)
+        dist = np.zeros(max(1, n - 1), np.int64)
+        ne = self.lib.kmsc_o_mst(_ptr(w, i64p), n, _ptr(edges, i32p), _ptr(dist, i64p))
+        return edges[:ne].copy(), dist[:ne].copy()
 
     def svb_encode(self, vals):
         vals = np.ascontiguousarray(vals, np.uint32)

@@ -184,6 +184,15 @@ static void TestKmerSetCompact() {  // test/kmer_set_compact.cc
     const auto c2 = KmerSetCompact<K, N, KeyType>::FromKmerSet(nc, false, true, 2);
     CHECK(c2.Size(1) == 20000 && nc.Equals(c2.ToKmerSet(false, 2), 2));
   }
+  {  // a blank line and a line shorter than K in an SPSS file: no k-mers from them, text preserved
+     // (the reference stores length - K mod 2^32 and recovers the length the same way,
+     // lib/core/kmer_set_compact.h:206-287)
+    const std::vector<std::string> lines = {"ACGTACGTACGT", "", "ACG", "TTTTTTTTTAC"};
+    const auto c3 = KmerSetCompact<K, N, KeyType>::FromStrings(lines);
+    CHECK(c3.ToStrings(1) == lines);
+    CHECK(c3.Weight() == 12 + 0 + 3 + 11);
+    CHECK(c3.ToKmerSet(false, 1).Size() == 4 + 3);  // 4 windows of the first line, 3 of the last, all distinct
+  }
 }
 
 static void TestKmerSetSet() {  // test/kmer_set_set.cc

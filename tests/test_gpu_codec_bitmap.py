@@ -110,3 +110,50 @@ def test_codec_rejects_corrupt_input(ctx, oracle):
     bad[48 + (1 << 14) // 4] ^= 0x7F
     with pytest.raises(kmsc.KmscError):
         ctx.codec_decode(bytes(bad))
+
+
+def _container(K, N, kb, n_keys, sizes, key_vals, oracle, n_sdata=None, n_kdata=None):
+    """a KMSC version-1 container put together by hand (layout: csrc/codec.cu)"""
+    import struct
+    nb = 1 << N
+
+    def stream(vals):  # 2-bit codes (bytes - 1), control bytes first, little-endian data
+        ctrl, data = bytearray((len(vals) + 3) // 4), bytearray()
+        for i, v in enumerate(vals):
+            c = 0 if v < (1 << 8) else 1 if v < (1 << 16) else 2 if v < (1 << 24) else 3
+            ctrl[i >> 2] |= c << (2 * (i & 3))
+            data += int(v).to_bytes(4, "little")[: c + 1]
+        return bytes(ctrl) + bytes(data), len(data)
+
+    s_enc, sd = stream(sizes)
+    k_enc, kd = stream(key_vals)
+    hdr = struct.pack("<IIIIIIQQQ", 0x43534D4B, 1, K, N, kb, 2 if kb == 8 else 1, n_keys,
+                      sd if n_sdata is None else n_sdata, kd if n_kdata is None else n_kdata)
+    return hdr + s_enc + k_enc
+
+
+def test_codec_rejects_sizes_that_only_add_up_mod_2_32(ctx, oracle):
+    """bucket sizes {0xFFFFFFFF, n_keys + 1, 0, ...} pass a 32-bit total check; a huge
+    n_sdata / n_kdata pair wraps the 64-bit length sum. Both must be refused before any key is written."""
+    import struct
+    import kmsc
+    K, N, kb, n_keys = 15, 14, 2, 5
+    nb = 1 << N
+    good = _container(K, N, kb, n_keys, [n_keys] + [0] * (nb - 1), [1, 2, 3, 4, 5], oracle)
+    magic = struct.unpack("<I", good[:4])[0]
+    ref = oracle.codec_encode(K, N, kb, np.array([0] + [n_keys] * nb, np.int64), np.array([1, 3, 6, 10, 15], np.uint16))
+    assert struct.unpack("<I", ref[:4])[0] == magic and ref == good, "hand-made container differs from the oracle's encoder"
+    assert ctx.codec_decode(good).Size() == n_keys
+    sizes = [0xFFFFFFFF, n_keys + 1] + [0] * (nb - 2)
+    assert sum(sizes) % (1 << 32) == n_keys
+    with pytest.raises(kmsc.KmscError):
+        ctx.codec_decode(_container(K, N, kb, n_keys, sizes, [1, 2, 3, 4, 5], oracle))
+    # lengths that only match modulo 2^64
+    true_sd, true_kd = nb, 5   # one data byte per small value
+    big = (1 << 64) - 4096
+    with pytest.raises(kmsc.KmscError):
+        ctx.codec_decode(_container(K, N, kb, n_keys, [n_keys] + [0] * (nb - 1), [1, 2, 3, 4, 5], oracle,
+                                    n_sdata=big, n_kdata=(true_sd + true_kd - big) % (1 << 64)))
+    # too many keys for one block (the encoder's own limit)
+    with pytest.raises(kmsc.KmscError):
+        ctx.codec_decode(_container(K, N, 8, (1 << 29) + 5, [n_keys] + [0] * (nb - 1), [1, 2, 3, 4, 5], oracle))
