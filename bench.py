@@ -20,10 +20,17 @@ fixed ("weak" scaling); the partial matrices are summed by one NCCL all-reduce.
            packed SPSS of every set (what KmerSetCompact holds in memory) is
            copied from pinned host memory, decoded to CSR on the device (P2), the
            matrix computed (P3) and read back.
-  --impl reference : the reference's own unmodified headers (oracle/_ref) running
-           KmerSetSet's constructor up to "calculated initial weights"
-           (GetSampledKmerSet per set + the all-pairs GetEdgeWeight loop over its
-           own 2 % bucket sample) on a bounded number of sets, all host threads.
+  --impl reference : the reference's own unmodified headers (oracle/_ref) on the SAME sets,
+           all host threads. Two like-for-like measurements:
+           exact   -- what the GPU arm computes: GetSampledKmerSet over ALL buckets for
+                      every set (one task per set, as kmer_set_set.h:138-153) + the
+                      all-pairs two-pointer merge (:158-219). The decode is timed on one
+                      wave of `cores` sets, each step times the pair loop on those sets,
+                      and `value` is the key-visits/s of the whole 64-set job at the
+                      measured phase rates (ceil(64 / cores) decode waves + all pairs).
+           sampled -- the reference's own constructor up to "calculated initial weights"
+                      (its 2 % bucket sample) on all 64 sets, once; the GPU arm reports
+                      the same job (`sampled`) with a 2 % bucket list of its own.
 """
 from __future__ import annotations
 
@@ -54,14 +61,17 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sets", type=int, default=64)
-    ap.add_argument("--kmers", type=int, default=10_000_000, help="k-mers per set per GPU")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"],
+                    help="C2 (BASELINE configs[1], the metric's config): 64 sets x 10M 23-mers per GPU, weak scaling; "
+                         "C3 (configs[2]): 256 sets x 10M 23-mers in all, prefix-sharded over the GPUs, strong scaling")
+    ap.add_argument("--sets", type=int, default=0, help="number of sets (default: 64 for C2, 256 for C3)")
+    ap.add_argument("--kmers", type=int, default=10_000_000, help="k-mers per set (C2: per GPU)")
     ap.add_argument("--p", type=float, default=0.002)
-    ap.add_argument("--ref-sets", type=int, default=0, help="sets in the reference sample (0 = auto)")
+    ap.add_argument("--no-ref-sampled", action="store_true", help="reference arm: skip the sampled-constructor run on all sets")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stage", action="store_true")
-    ap.add_argument("--no-allreduce", action="store_true", help="diagnostic: time the per-rank partial matrices only")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle check of W at full size")
     ap.add_argument("--emulate", default="", help="diagnostic, one GPU: R/W = the shard rank R of a W-rank job would hold")
     return ap.parse_args()
 
@@ -151,60 +161,113 @@ class ClockSampler:
 # reference arm / cpu baseline
 # ----------------------------------------------------------------------------
 
-def reference_run(n_sets_sample, G, p, steps, warmup, n_workers):
-    """Times the reference's own constructor phases on `n_sets_sample` sets of the workload."""
+def gen_codes(n_sets, G, p):
+    """the workload's sequences as numpy code arrays (0..3). Generated with torch on the GPU when
+    there is one (then they are the very sets the GPU arm uses), else with the numpy generator of
+    synth.py (same distribution, other sets)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+            return [s.cpu().numpy() for s in gen_sequences_torch(n_sets, G, p, dev)], "torch-cuda generator (the GPU arm's sets)"
+    except Exception:
+        pass
     import synth
-    from _oracle import Ref, set_ref_seed
+    return synth.phylogeny_sequences(n_sets, G, p), "numpy generator (same distribution, other sets than the GPU arm)"
+
+
+def write_spss(codes, path, piece=100000):
+    """one sequence as an SPSS-like text file: overlapping pieces spelling the same k-mers"""
+    import synth
+    with open(path, "wb") as fh:
+        for s in synth.split_strings(codes, K, piece):
+            fh.write(s + b"\n")
+
+
+def reference_exact(seqs, steps, warmup, cores, n_total):
+    """The GPU arm's job with the reference's code: all-bucket GetSampledKmerSet per set (reference
+    lib/core/kmer_set_compact.h:120-203, one task per set as kmer_set_set.h:143-152) timed on ONE
+    wave of min(cores, n) sets, then `steps` timed passes of the all-pairs two-pointer merge
+    (kmer_set_set.h:158-219; the constructor's lambda cannot be handed all buckets, so the loop is
+    the oracle's restatement of it, pthreads over the pairs) over those sets. Returns the phase
+    rates and the projection to n_total sets."""
+    import concurrent.futures as cf
+    import synth
+    from _oracle import Oracle, Ref
+    o = Oracle()
+    have_ref = Ref.available()
+    ref = Ref() if have_ref else None
+    n_w = min(cores, len(seqs))
+    ids = np.arange(1 << N, dtype=np.int32)
+    strings = [[p.decode() for p in synth.split_strings(s, K, 100000)] for s in seqs[:n_w]]
+
+    def decode(i):
+        if have_ref:
+            offs, keys, _, _ = ref.sampled_set(4, strings[i], True, ids, n_workers=1)
+        else:
+            offs, keys = o.sampled_set(strings[i], K, N, True, ids)
+        return offs, keys
+
+    t0 = time.time()
+    with cf.ThreadPoolExecutor(n_w) as ex:  # ctypes releases the GIL: one reference task per thread
+        dec = list(ex.map(decode, range(n_w)))
+    t_wave = time.time() - t0
+    offs_l = [d[0] for d in dec]
+    keys_l = [d[1].astype(np.uint32) for d in dec]   # the reference's KeyType for K = 23 (vector<uint32_t> buckets)
+    times, visits = [], 0
+    for it in range(warmup + steps):
+        t0 = time.time()
+        _, visits = o.pair_counts(offs_l, keys_l, KB, 1 << N, n_threads=cores)
+        if it >= warmup:
+            times.append(time.time() - t0)
+    pair_rate = visits * len(times) / sum(times)
+    keys_per_set = float(np.mean([int(o_[-1]) for o_ in offs_l]))
+    visits_full = (n_total - 1) * keys_per_set * n_total
+    waves = -(-n_total // cores)
+    t_full = waves * t_wave + visits_full / pair_rate
+    return {"kind": "reference" if have_ref else "port", "t_decode_wave_s": t_wave, "wave_sets": n_w, "pair_rate": pair_rate,
+            "pair_step_s": float(np.mean(times)), "visits_step": int(visits), "visits_full": visits_full,
+            "t_full_s": t_full, "value": visits_full / t_full, "waves": waves}
+
+
+def reference_sampled(seqs, cores):
+    """the reference's own constructor (lib/core/kmer_set_set.h:109-221) up to 'calculated initial
+    weights' on ALL sets: GetSampledKmerSet over its 2 % bucket sample + all-pairs GetEdgeWeight"""
+    from _oracle import Oracle, Ref, set_ref_seed
+    if not Ref.available():
+        return None
     set_ref_seed(4242)
     ref = Ref()
     ref.lib.ref_set_log_level(4)
-    seqs = synth.phylogeny_sequences(n_sets_sample, G, p)
+    o = Oracle()
     tmp = tempfile.mkdtemp(prefix="kmsc_ref_")
-    files, lens = [], []
+    files = []
     for i, s in enumerate(seqs):
         f = os.path.join(tmp, f"{i}.txt")
-        with open(f, "wb") as fh:
-            for piece in synth.split_strings(s, K, 100000):  # an SPSS-like multi-string file
-                fh.write(piece + b"\n")
+        write_spss(s, f)
         files.append(f)
-        km = synth.kmers_of(s, K, True)  # duplicates kept, like GetSampledKmerSet
-        lens.append(np.bincount((km >> np.uint64(2 * K - N)).astype(np.int64), minlength=1 << N))
-    lens = np.stack(lens)
-    times, visits = [], []
-    for it in range(warmup + steps):
-        c0 = ref.seed_counter()
-        out = ref.kmer_set_set(4, files, True, n_workers=n_workers, stop_after_weights=True)
-        assert out["rc"] == 1, out["rc"]
-        ids = ref.random_ints(c0, (1 << N) // 50, 0, (1 << N) - 1)
-        v = (n_sets_sample - 1) * int(lens[:, ids].sum())
-        if it >= warmup:
-            times.append(out["phase_s"][0] + out["phase_s"][1])
-            visits.append(v)
+    c0 = ref.seed_counter()
+    out = ref.kmer_set_set(4, files, True, n_workers=cores, stop_after_weights=True)
     for f in files:
         os.remove(f)
     os.rmdir(tmp)
-    return sum(visits) / sum(times), float(np.mean(times)), times
-
-
-def port_run(n_sets_sample, G, p, n_threads):
-    """fallback CPU baseline: the oracle's merge loop (kmsc_oracle.c) on all buckets"""
-    import synth
-    from _oracle import Oracle
-    o = Oracle()
-    seqs = synth.phylogeny_sequences(n_sets_sample, G, p)
-    offs_l, keys_l = [], []
-    for s in seqs:
-        offs, keys = synth.csr_of(synth.kmer_set_of(s, K), K, N, KB)
-        offs_l.append(offs)
-        keys_l.append(keys)
-    t = time.time()
-    _, v = o.pair_counts(offs_l, keys_l, KB, 1 << N, n_threads=n_threads)
-    dt = time.time() - t
-    return v / dt, dt
+    if out["rc"] != 1:
+        return None
+    ids = ref.random_ints(c0, (1 << N) // 50, 0, (1 << N) - 1)
+    keys = sum(int(o.bucket_histogram(s, K, N)[ids].sum()) for s in seqs)
+    v = (len(seqs) - 1) * keys
+    t = out["phase_s"][0] + out["phase_s"][1]
+    return {"value": v / t, "unit": UNIT, "seconds": t, "decode_s": out["phase_s"][0], "weights_s": out["phase_s"][1],
+            "n_sets": len(seqs), "n_buckets": int(len(ids)), "key_visits": int(v),
+            "what": "reference KmerSetSet constructor up to 'calculated initial weights' (its own 2% bucket sample), "
+                    f"all {len(seqs)} sets, n_workers={cores}"}
 
 
 def main():
     args = parse_args()
+    strong = args.workload == "C3"
+    if args.sets <= 0:
+        args.sets = 256 if strong else 64
     # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version
     # banner, for one) goes to stderr instead
     out = os.fdopen(os.dup(1), "w")
@@ -214,35 +277,41 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     G = args.kmers + K - 1  # bases per set per GPU
     cores = os.cpu_count() or 1
-    config = {"workload": f"C2: {args.sets} sets x {args.kmers} canonical {K}-mers per GPU (<{K},{N},uint32>), "
-                          f"binary phylogeny p={args.p}, all-pairs intersection matrix over all {1 << N} buckets (exact)",
-              "n_sets": args.sets, "kmers_per_set_per_gpu": args.kmers, "k": K, "bucket_bits": N,
-              "parallelism": f"prefix-sharded x{world}" if world > 1 else "single GPU",
-              "l2": "inputs (2.56 GB/GPU) exceed the 126 MB L2; no flush needed"}
+    config = {"workload": (f"C3: {args.sets} sets x {args.kmers} canonical {K}-mers in all (<{K},{N},uint32>), "
+                           if strong else
+                           f"C2: {args.sets} sets x {args.kmers} canonical {K}-mers per GPU (<{K},{N},uint32>), ")
+                          + f"binary phylogeny p={args.p}, all-pairs intersection matrix over all {1 << N} buckets (exact)",
+              "n_sets": args.sets, ("kmers_per_set" if strong else "kmers_per_set_per_gpu"): args.kmers, "k": K, "bucket_bits": N,
+              "parallelism": f"prefix-sharded x{world}, all-reduce inside kmsc_pair_counts" if world > 1 else "single GPU",
+              "l2": f"inputs ({args.sets * args.kmers * 4 / (1 if not strong else world) / 1e9:.2f} GB/GPU) exceed the 126 MB L2; no flush needed"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        from _oracle import Ref
-        n_s = args.ref_sets or (8 if args.steps + args.warmup <= 16 else 4 if args.steps + args.warmup <= 40 else 2)
-        n_s = min(n_s, args.sets)
-        if Ref.available():
-            val, mean_s, _ = reference_run(n_s, G, args.p, args.steps, args.warmup, cores)
-            kind = "reference"
-            sample = (f"first {n_s} of the {args.sets} sets; KmerSetSet constructor up to 'calculated initial weights' "
-                      f"(GetSampledKmerSet + all-pairs GetEdgeWeight) over the reference's own 2% bucket sample "
-                      f"({(1 << N) // 50} of {1 << N} buckets), n_workers={cores}")
-        else:
-            val, mean_s = port_run(n_s, G, args.p, cores)
-            kind = "port"
-            sample = f"first {n_s} sets, all buckets, oracle merge loop, {cores} threads"
+        seqs, how = gen_codes(args.sets, G, args.p)
+        ex = reference_exact(seqs, args.steps, args.warmup, cores, args.sets)
+        # N ranks: the GPU arm's job holds `world` times the k-mers per set (weak scaling); both
+        # reference phases are linear in the sequence length, so the measured rates are scaled
+        visits_full = ex["visits_full"] * world
+        t_full = ex["waves"] * ex["t_decode_wave_s"] * world + visits_full / ex["pair_rate"]
+        val = visits_full / t_full
+        smp = None if args.no_ref_sampled else reference_sampled(seqs, cores)
+        sample = (f"exact job of the config with the reference's code: GetSampledKmerSet over all {1 << N} buckets timed on one "
+                  f"wave of {ex['wave_sets']} of the {args.sets} sets ({ex['t_decode_wave_s']:.2f} s, one task per set), then each step = "
+                  f"the all-pairs two-pointer merge over those {ex['wave_sets']} sets on {cores} threads ({ex['pair_step_s']:.3f} s, "
+                  f"{ex['pair_rate']:.3e} key-visits/s); value = key-visits of the whole {args.sets}-set job / "
+                  f"({ex['waves']} decode waves + all pairs at that rate) = {t_full:.1f} s per job"
+                  + (f", sequence length scaled x{world}" if world > 1 else "") + f"; data: {how}")
+        cfg = dict(config)
+        cfg["reference_sample"] = sample
         line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "impl": "reference",
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ex["kind"], "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "phases": {k: ex[k] for k in ("t_decode_wave_s", "wave_sets", "waves", "pair_rate", "pair_step_s", "visits_step")},
+                "sampled": smp, "gpu_launches": 0}
         print(json.dumps(line), file=out, flush=True)
         return
 
@@ -260,14 +329,25 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx = kmsc.Context(local_rank, stream.cuda_stream)
+    if world > 1:
+        # the library owns the communicator: the id travels through torch.distributed once
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(kmsc.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
 
     # data: genome grows with the number of ranks; every rank builds the same sequences
     shard_rank, shard_world = rank, world
     if args.emulate and world == 1:
         shard_rank, shard_world = (int(x) for x in args.emulate.split("/"))
-    Gtot = args.kmers * shard_world + K - 1
+    Gtot = args.kmers * (1 if strong else shard_world) + K - 1
     seqs = gen_sequences_torch(args.sets, Gtot, args.p, dev)
     str_offs = np.array([0, Gtot], np.int64)
+    # CPU copies for the checks outside the timed regions: the oracle check of W and the CPU baseline
+    check_ids = sorted({0, 1, 2, args.sets - 2, args.sets - 1} & set(range(args.sets)))
+    keep = set(check_ids) | (set(range(min(cores, args.sets))) if world == 1 and not args.no_cpu_baseline else set())
+    codes_cpu = {i: seqs[i].cpu().numpy() for i in sorted(keep)} if world == 1 else {}
     pinned, nbytes_in = [], 0
     for s in seqs:
         w = pack_torch(s)
@@ -300,9 +380,7 @@ def main():
     visits_local = (n - 1) * keys_local
 
     def step_resident():
-        ctx.pair_counts_device(sets, d_out.data_ptr())
-        if world > 1 and not args.no_allreduce:
-            dist.all_reduce(d_out)
+        ctx.pair_counts_device(sets, d_out.data_ptr())   # N > 1: the partial matrices are all-reduced inside
 
     def barrier():
         if world > 1:
@@ -349,6 +427,29 @@ def main():
     value = visits_total * args.steps / (ms / 1e3)
     W = d_out.cpu().numpy().reshape(n, n)
 
+    # ---- parity at full size, outside the timed region: entries of W against the oracle's two-pointer
+    # merge (reference kmer_set_set.h:158-184) over k-mer sets extracted on the CPU with numpy from the
+    # same sequences. A mismatch fails the run.
+    oracle_check = None
+    if world == 1 and not args.no_check and len(check_ids) >= 2:
+        import synth
+        from _oracle import Oracle
+        o = Oracle()
+        ksets = {i: synth.kmer_set_of(codes_cpu[i], K, True) for i in check_ids}
+        checked = []
+        for i in check_ids:
+            assert int(W[i, i]) == len(ksets[i]), f"W[{i},{i}] = {int(W[i, i])} but the set holds {len(ksets[i])} k-mers"
+            checked.append([i, i, int(W[i, i])])
+        for a in range(len(check_ids)):
+            for b in range(a + 1, len(check_ids)):
+                i, j = check_ids[a], check_ids[b]
+                want = int(o.merge_count(ksets[i], ksets[j]))
+                assert int(W[i, j]) == want and int(W[j, i]) == want, f"W[{i},{j}] = {int(W[i, j])}, oracle {want}"
+                checked.append([i, j, want])
+        oracle_check = {"entries": len(checked), "ok": True, "W_0_last": int(W[0, n - 1]),
+                        "how": "numpy k-mer sets of the same sequences + oracle merge_count; every listed entry equal"}
+        del ksets
+
     # ---- "pairwise-weight plus diff" stage: the matrix + one split per spanning-tree edge ----
     # (north_star: MST over d(i,j) = |Si| + |Sj| - 2 W[i][j]; per edge the two difference sets
     # via kmsc_pair_split). Bytes are the algorithmic B_w + sum B_s of SURVEY 8(d).
@@ -372,7 +473,7 @@ def main():
         W_loc = W
         if world > 1:  # W is the all-reduced matrix; the hints are this rank's partial counts
             d_loc = torch.zeros(n * n, dtype=torch.int64, device=dev)
-            ctx.pair_counts_device(sets, d_loc.data_ptr())
+            ctx.pair_counts_device(sets, d_loc.data_ptr(), partial=True)
             W_loc = d_loc.cpu().numpy().reshape(n, n)
         hint = np.array([W_loc[pa, ch] for pa, ch in edges], np.int64)
         for _ in range(2):  # warm-up (allocation pool, first-launch attributes)
@@ -401,6 +502,7 @@ def main():
 
     # ---- e2e: host packed SPSS -> device CSR -> matrix -> host ------------------------
     e2e = None
+    sampled = None
     if not args.no_e2e:
         e2e_steps = max(2, min(args.steps, 5))
         host_out = np.zeros((n, n), np.int64)
@@ -408,8 +510,6 @@ def main():
         def step_e2e_single():
             ss = build_sets()
             ctx.pair_counts_device(ss, d_out.data_ptr())
-            if world > 1:
-                dist.all_reduce(d_out)
             host_out[:] = d_out.cpu().numpy().reshape(n, n)
             for s in ss:
                 s.free()
@@ -424,39 +524,9 @@ def main():
 
         def step_e2e_exchange():
             mine = [rank + j * world for j in range(m_own)]
-            full = [ctx.set_from_packed(K, N, KB, None, str_offs, words_ptr=pinned[i].data_ptr()) for i in mine]
-            ko = np.stack([ctx.set_bucket_offsets(s, cuts_np) for s in full])       # [m_own][world + 1]
-            sizes = (ko[:, 1:] - ko[:, :-1]).astype(np.int64)                        # keys of own set j for rank q
-            t_send_sz = torch.from_numpy(np.ascontiguousarray(sizes.T)).to(dev)      # [world][m_own], dest-major
-            t_recv_sz = torch.empty_like(t_send_sz)
-            dist.all_to_all_single(t_recv_sz, t_send_sz)
-            recv_sz = t_recv_sz.cpu().numpy()                                        # [src][j]
-            nbq = [int(cuts[q + 1] - cuts[q]) + 1 for q in range(world)]
-            nb_me = nbq[rank]
-            in_k = [int(sizes[:, q].sum()) for q in range(world)]
-            out_k = [int(recv_sz[r].sum()) for r in range(world)]
-            send_keys = torch.empty(max(1, sum(in_k)), dtype=torch.int32, device=dev)
-            recv_keys = torch.empty(max(1, sum(out_k)), dtype=torch.int32, device=dev)
-            send_offs = torch.empty(m_own * sum(nbq), dtype=torch.int32, device=dev)
-            recv_offs = torch.empty(world * m_own * nb_me, dtype=torch.int32, device=dev)
-            kp, op = 0, 0
-            for q in range(world):
-                for j, s in enumerate(full):
-                    ctx.set_export_range(s, int(cuts[q]), int(cuts[q + 1]), int(ko[j, q]), int(ko[j, q + 1]),
-                                         send_offs.data_ptr() + op * 4, send_keys.data_ptr() + kp * KB)
-                    kp += int(sizes[j, q]); op += nbq[q]
-            dist.all_to_all_single(recv_keys[:sum(out_k)], send_keys[:sum(in_k)], out_k, in_k)
-            dist.all_to_all_single(recv_offs, send_offs, [m_own * nb_me] * world, [m_own * x for x in nbq])
-            ss = [None] * n
-            kp = 0
-            for r in range(world):
-                for j in range(m_own):
-                    cnt = int(recv_sz[r, j])
-                    ss[r + j * world] = ctx.set_import_range(K, N, KB, lo, hi, recv_offs.data_ptr() + (r * m_own + j) * nb_me * 4,
-                                                             recv_keys.data_ptr() + kp * KB, cnt)
-                    kp += cnt
+            full = ctx.sets_from_packed_batch(K, N, KB, None, [str_offs] * m_own, words_ptrs=[pinned[i].data_ptr() for i in mine])
+            ss = ctx.sets_exchange(full, cuts_np, n)     # one grouped NCCL exchange inside the library
             ctx.pair_counts_device(ss, d_out.data_ptr())
-            dist.all_reduce(d_out)
             host_out[:] = d_out.cpu().numpy().reshape(n, n)
             for s in ss + full:
                 s.free()
@@ -478,9 +548,32 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt[0])
         assert np.array_equal(host_out, W), "e2e matrix differs from the resident run"
+        # the reference's own mode: weights over a 2 % bucket sample (kmer_set_set.h:123-124), same sets
+        if world == 1:
+            ids = np.sort(np.random.default_rng(4242).choice(1 << N, (1 << N) // 50, replace=False)).astype(np.int32)
+
+            def step_sampled():
+                ss = build_sets()
+                ctx.pair_counts_device(ss, d_out.data_ptr(), bucket_ids=ids)
+                host_out[:] = d_out.cpu().numpy().reshape(n, n)
+                for s in ss:
+                    s.free()
+            step_sampled()
+            barrier()
+            e0.record(stream)
+            for _ in range(e2e_steps):
+                step_sampled()
+            e1.record(stream)
+            barrier()
+            ms_s = e0.elapsed_time(e1) / e2e_steps
+            v_s = (n - 1) * int(np.trace(host_out))
+            sampled = {"value": v_s / (ms_s / 1e3), "unit": UNIT, "ms_per_step": ms_s, "n_buckets": int(len(ids)), "key_visits": v_s,
+                       "what": "host packed SPSS -> device sets -> matrix over a 2% bucket sample -> host (the reference "
+                               "constructor's own job up to 'calculated initial weights'; compare with the reference arm's `sampled`)"}
         e2e = {"value": visits_total * e2e_steps / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(nbytes_in // world) if m_own > 0 else int(nbytes_in),
-               "how": ("decode split by set over the ranks + one all-to-all of prefix slices (NCCL) + all-reduce of the partial matrices"
+               "how": ("decode split by set over the ranks (kmsc_sets_from_packed_batch) + kmsc_sets_exchange (one grouped NCCL send/recv of "
+                       "the prefix slices) + kmsc_pair_counts_device (all-reduce inside)"
                        if m_own > 0 else "every rank decodes its prefix range of every set"),
                "d2h_bytes_per_step": int(n * n * 8), "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps}
 
@@ -520,25 +613,23 @@ def main():
         stage["frac_of_hbm_peak"] = stage["achieved_gbs"] / peak
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        from _oracle import Ref
         try:
-            if Ref.available():
-                v, mean_s, _ = reference_run(4, G, args.p, 1, 0, cores)
-                cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                                "sample": "first 4 of the sets; reference KmerSetSet constructor up to 'calculated "
-                                          f"initial weights' over its own 2% bucket sample, n_workers={cores}; "
-                                          f"{mean_s:.1f} s"}
-            else:
-                v, dt = port_run(8, G, args.p, cores)
-                cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"first 8 sets, all buckets, oracle merge loop; {dt:.1f} s"}
+            n_w = min(cores, args.sets)
+            ex = reference_exact([codes_cpu[i] for i in range(n_w)], 2, 0, cores, args.sets)
+            cpu_baseline = {"value": ex["value"], "unit": UNIT, "cores": cores, "kind": ex["kind"],
+                            "sample": f"the reference's code on {n_w} of the {args.sets} sets: all-bucket GetSampledKmerSet, one task per set "
+                                      f"({ex['t_decode_wave_s']:.1f} s per wave), 2 passes of the all-pairs two-pointer merge over them "
+                                      f"({ex['pair_rate']:.3e} key-visits/s on {cores} threads); value = the whole {args.sets}-set job at "
+                                      f"those rates ({ex['t_full_s']:.1f} s). bench.py --impl reference is the full arm"}
         except Exception as ex:  # the baseline must never take the bench line down
             cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage": stage, "cpu_baseline": cpu_baseline,
+            "sampled": sampled, "oracle_check": oracle_check,
             "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local),
                       "p3_stats": ctx.pair_counts_stats() if args.no_e2e and args.no_stage else None, "buckets": [int(lo), int(hi)]}}
     if per_rank is not None:

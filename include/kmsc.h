@@ -21,11 +21,15 @@
  *    sizeof(KeyType): 2, 4 or 8 (uint16/uint32/uint64 as in
  *    src/kmerset-multiple-compress.cc:149-157; uint64 for K=31).
  *  - Host buffers belong to the caller; device buffers belong to the library
- *    until the matching *_free. Calls are synchronous at return unless the name
- *    ends in _async / _device (those enqueue on the context's stream).
+ *    until the matching *_free. Calls that return host data are synchronous at
+ *    return. Calls that only produce device sets (kmsc_sets_from_packed_batch,
+ *    kmsc_sets_exchange, kmsc_pair_split*) may return with work still queued on the
+ *    context's stream: the sets are valid for every later call on that context,
+ *    and kmsc_ctx_sync waits for them. kmsc_pair_counts_device synchronises once
+ *    internally (tile statistics) and leaves the matrix on the stream.
  *  - One kmsc_ctx = one GPU + one stream; drive it from one host thread.
- *    Multi-GPU = one context per process/rank, sets restricted to that rank's
- *    bucket range, partial matrices summed by the caller's all-reduce.
+ *    Multi-GPU = one context per process/rank (kmsc_comm_init), sets restricted
+ *    to that rank's bucket range, partial matrices summed inside kmsc_pair_counts*.
  */
 #ifndef KMSC_H_
 #define KMSC_H_
@@ -95,6 +99,27 @@ int kmsc_set_export_range(kmsc_ctx* ctx, const kmsc_set* set, int32_t bucket_lo,
 int kmsc_set_import_range(kmsc_ctx* ctx, int K, int N, int key_bytes, int32_t bucket_lo, int32_t bucket_hi,
                           const uint32_t* d_offs, const void* d_keys, int64_t n_keys, kmsc_set** out);
 
+/* ---- multi-GPU inside the library: one context per rank, NCCL communicator owned by the context ---- */
+/* The reference is one shared-memory process (boost::asio::thread_pool, 40 call sites); what shards is
+ * the sum over buckets of lib/core/kmer_set_set.h:161-181. With a communicator on the context,
+ * kmsc_pair_counts / _device / _rows all-reduce the per-rank partial matrices INSIDE the call (one
+ * ncclAllReduce of n*n int64 on the context's stream), so every rank returns the full matrix.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls fail with KMSC_E_STATE.
+ * id128: 128 bytes from kmsc_comm_unique_id on one rank, handed to every rank by the host program
+ * (MPI, torch.distributed, a file, or plain memory between threads). */
+int kmsc_comm_unique_id(void* id128);
+int kmsc_comm_init(kmsc_ctx* ctx, int rank, int n_ranks, const void* id128);
+int kmsc_comm_destroy(kmsc_ctx* ctx);
+int kmsc_comm_info(kmsc_ctx* ctx, int* rank, int* n_ranks);
+/* Every rank decoded n_mine WHOLE sets (global set index = rank + j * n_ranks for its j-th set) and
+ * receives all n_total = n_mine * n_ranks sets restricted to ITS bucket range [cuts[rank],
+ * cuts[rank+1]) (cuts: n_ranks + 1 ascending bucket indices from 0 to 2^N, the same on all ranks).
+ * One table all-gather + one host synchronisation (the sizes), then one grouped ncclSend / ncclRecv
+ * moves every slice straight between the sets' key arrays. Replaces kmsc_set_bucket_offsets /
+ * _export_range / _import_range + a caller-side all-to-all. out: n_total handles. */
+int kmsc_sets_exchange(kmsc_ctx* ctx, const kmsc_set* const* mine, int32_t n_mine, const int32_t* cuts,
+                       kmsc_set** out, int32_t n_total);
+
 /* ---- P2: SPSS text -> device set ------------------------------------------------ */
 /* Replaces KmerSetCompact::GetSampledKmerSet (lib/core/kmer_set_compact.h:120-203;
  * dedup = 0: duplicates kept) and KmerSetCompact::ToKmerSet / GetKmerSetFromSPSS
@@ -147,12 +172,21 @@ int kmsc_set_neighbors(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int32_
  * Any n: up to 256 sets are one pass; more are covered by pairs of 128-set groups. */
 int kmsc_pair_counts(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                      const int32_t* bucket_ids, int32_t n_ids, int64_t* out, int64_t* key_visits);
-/* Same, result left in DEVICE memory d_out (n*n int64, on the context's stream):
- * the per-rank partial a caller all-reduces (NCCL) across a prefix-sharded job. */
+/* Same, result left in DEVICE memory d_out (n*n int64, on the context's stream). On a context with
+ * a communicator (kmsc_comm_init) the per-rank partial matrices are summed by one ncclAllReduce
+ * inside the call: every rank ends with the full matrix. */
 int kmsc_pair_counts_device(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                             const int32_t* bucket_ids, int32_t n_ids, int64_t* d_out);
+/* This rank's PARTIAL matrix only (no all-reduce even with a communicator), in device memory:
+ * |S_i & S_j| inside the rank's bucket range = the exact inter_hint of kmsc_pair_split_batch on
+ * a prefix shard. */
+int kmsc_pair_counts_partial(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                             const int32_t* bucket_ids, int32_t n_ids, int64_t* d_out);
 /* Row mode (lib/core/kmer_set_set.h:385-425, the 3n-2 re-weights after a merge):
- * out[r*n + l] = weight(rows[r], l) for l in [0, n). */
+ * out[r*n + l] = weight(rows[r], l) for l in [0, n). Every column set is read once and merged
+ * (the reference's two-pointer loop, :165-180: duplicates count with min multiplicity) against
+ * the row sets' runs staged in shared memory -- 3 rows cost one pass over the sets, not a full
+ * n x n matrix. All-reduced over the ranks like kmsc_pair_counts. */
 int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                           const int32_t* rows, int32_t n_rows, const int32_t* bucket_ids,
                           int32_t n_ids, int64_t* out);

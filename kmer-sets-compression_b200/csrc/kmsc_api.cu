@@ -264,6 +264,14 @@ int set_build_levels(kmsc_ctx* ctx, kmsc_set* s) {
   }
 }
 
+int set_ensure_levels(kmsc_ctx* ctx, const kmsc_set* cs) {
+  if (!cs || cs->fine_ready) return KMSC_OK;
+  kmsc_set* s = const_cast<kmsc_set*>(cs);
+  KMSC_TRY(set_build_levels(ctx, s));
+  s->fine_ready = true;
+  return KMSC_OK;
+}
+
 int set_derive_levels(kmsc_ctx* ctx, kmsc_set* s) {
   if (s->max_level == 0) return KMSC_OK;
   uint64_t entries = levels_total_entries(s->N, s->max_level - 1);
@@ -357,6 +365,7 @@ void kmsc_ctx_destroy(kmsc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  kmsc_comm_destroy(ctx);
   ctx->plan.release(); ctx->work.release(); ctx->work2.release(); ctx->work3.release(); ctx->stage.release(); ctx->small.release(); for (int i = 0; i < kmsc_ctx::kP2Slots; i++) {
     ctx->p2a[i].release(); ctx->p2b[i].release(); ctx->p2tab[i].release(); ctx->p2rb[i].release();
     if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);

@@ -72,6 +72,9 @@ struct kmsc_ctx {
   cudaStream_t copy_stream = nullptr;  // host-to-device copies of a batch decode
   cudaEvent_t copy_ev[kP2Slots] = {};  // "group g is on the device"
   cudaEvent_t fence_ev = nullptr;
+  // multi-GPU: NCCL communicator of this rank (comm.cu); NULL = single GPU
+  void* comm = nullptr;
+  int comm_rank = 0, comm_ranks = 1;
   void* pinned = nullptr; // pinned host staging
   size_t pinned_cap = 0;
   // pair_counts: redundancy (keys per distinct key in a tile) seen by the last call
@@ -102,6 +105,7 @@ struct kmsc_set {
   uint32_t* lev_base = nullptr;  // device, all levels in one allocation
   uint32_t* lev[kmsc::kMaxFineLevel + 1] = {};
   int has_dups = -1;      // -1 unknown, 0 no, 1 yes
+  bool fine_ready = true; // false: only lev[0] is filled (lean split output); set_ensure_levels builds the rest
   // buckets outside [b_lo, b_hi) are known to be empty (a rank's prefix shard); -1 = all buckets
   int32_t b_lo = -1, b_hi = -1;
 };
@@ -110,6 +114,8 @@ namespace kmsc {
 
 int ctx_pinned(kmsc_ctx* ctx, size_t bytes, void** out);
 inline void count_launch(kmsc_ctx* ctx, int n = 1) { ctx->launches += n; }
+// sums a device array over the ranks of the context's communicator, in place (no-op without one)
+int comm_allreduce_u64(kmsc_ctx* ctx, unsigned long long* d_buf, size_t count);
 
 // set construction helpers (set_build.cu)
 int set_alloc(kmsc_ctx* ctx, int K, int N, int key_bytes, int64_t n_keys, kmsc_set** out);
@@ -118,6 +124,8 @@ int set_build_levels(kmsc_ctx* ctx, kmsc_set* s);
 // given lev[max_level] (finest) already filled, derive coarser levels by striding
 int set_derive_levels(kmsc_ctx* ctx, kmsc_set* s);
 int set_check_dups(kmsc_ctx* ctx, kmsc_set* s);
+// builds lev[1..max_level] of a set that only carries lev[0] (no-op otherwise); call before reading a finer level
+int set_ensure_levels(kmsc_ctx* ctx, const kmsc_set* s);
 // union of two counted sets with saturating uint8 counts (set_ops.cu); counts are device arrays
 // aligned with the keys; *out_counts is cudaMalloc'd
 int counted_union(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kmsc_set* b, const uint8_t* cb,

@@ -948,6 +948,7 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, 
                      const uint32_t* h_bitmap, unsigned long long L, double keys_in_phase,
                      unsigned long long* d_W, unsigned long long host_stats[4]) {
   const kmsc_set* s0 = sets[0];
+  for (int i = 0; i < n; i++) KMSC_TRY(set_ensure_levels(ctx, sets[i]));
   const int nb = 1 << s0->N;
   int f = 0;
   {
@@ -1257,6 +1258,13 @@ extern "C" {
 
 int kmsc_pair_counts_device(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
                             const int32_t* bucket_ids, int32_t n_ids, int64_t* d_out) {
+  KMSC_TRY(pair_counts_run(ctx, sets, n, bucket_ids, n_ids, (unsigned long long*)d_out));
+  // a rank of a prefix-sharded job: the partial matrices are summed here, one all-reduce
+  return comm_allreduce_u64(ctx, (unsigned long long*)d_out, (size_t)n * n);
+}
+
+int kmsc_pair_counts_partial(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
+                             const int32_t* bucket_ids, int32_t n_ids, int64_t* d_out) {
   return pair_counts_run(ctx, sets, n, bucket_ids, n_ids, (unsigned long long*)d_out);
 }
 
@@ -1266,6 +1274,7 @@ int kmsc_pair_counts(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
   KMSC_TRY(ctx->work.reserve((size_t)n * n * 8));
   unsigned long long* d_W = (unsigned long long*)ctx->work.p;
   KMSC_TRY(pair_counts_run(ctx, sets, n, bucket_ids, n_ids, d_W));
+  KMSC_TRY(comm_allreduce_u64(ctx, d_W, (size_t)n * n));
   KMSC_CUDA(cudaMemcpyAsync(out, d_W, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
   if (key_visits) {
@@ -1287,21 +1296,5 @@ int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8) {
 }
 
 int kmsc_pair_counts_build(kmsc_ctx* ctx) { return ctx ? ctx->pc_last_build : -1; }
-
-int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
-                          const int32_t* rows, int32_t n_rows, const int32_t* bucket_ids,
-                          int32_t n_ids, int64_t* out) {
-  if (!ctx || !out || !rows || n < 1 || n_rows < 0) { set_error("bad argument"); return KMSC_E_INVALID; }
-  for (int r = 0; r < n_rows; r++)
-    if (rows[r] < 0 || rows[r] >= n) { set_error("row %d out of range", rows[r]); return KMSC_E_INVALID; }
-  KMSC_TRY(ctx->work.reserve((size_t)n * n * 8));
-  unsigned long long* d_W = (unsigned long long*)ctx->work.p;
-  KMSC_TRY(pair_counts_run(ctx, sets, n, bucket_ids, n_ids, d_W));
-  for (int r = 0; r < n_rows; r++)
-    KMSC_CUDA(cudaMemcpyAsync(out + (size_t)r * n, d_W + (size_t)rows[r] * n, (size_t)n * 8,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
-  return KMSC_OK;
-}
 
 }  // extern "C"

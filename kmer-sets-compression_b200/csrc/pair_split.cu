@@ -91,7 +91,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kernel(
     const SplitPair* __restrict__ pairs, uint32_t n_pairs, uint32_t chunks_per_pair, uint32_t NF, int N, int F,
     int key_bits, int qlog_live, uint32_t xlo, uint32_t xhi, unsigned long long* __restrict__ state,
-    uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
+    uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals, int lean) {
   uint32_t* const watchdog = ticket + 1;
   __shared__ uint32_t s_w[kSpThreads / 32];
   __shared__ uint32_t s_unit;
@@ -222,7 +222,11 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
       if (c == chunks_per_pair - 1) {
         totals[p * 3 + 0] = eI + totI; totals[p * 3 + 1] = eA + totA; totals[p * 3 + 2] = eB + totB;
         for (int q = 0; q < 3; q++)
-          if (P->lev[q]) write_levels(P->lev[q], N, F, NF, q == 0 ? eI + totI : q == 1 ? eA + totA : eB + totB);
+          if (P->lev[q]) {
+            const uint32_t tot_q = q == 0 ? eI + totI : q == 1 ? eA + totA : eB + totB;
+            if (lean) P->lev[q][(size_t)1 << N] = tot_q;   // lean: only the bucket level is written
+            else write_levels(P->lev[q], N, F, NF, tot_q);
+          }
       }
     }
   }
@@ -242,6 +246,16 @@ __global__ void __launch_bounds__(kSpThreads, KMSC_SPLIT_MINB) split_stream_kern
     uint32_t* const l2 = P->lev[2];
     const int tz = sub ? -1 : x ? min(F, __ffs(x) - 1) : F;  // levels F, F-1, ..., F-tz have an entry at x
     size_t start = ((size_t)1 << N) * (((size_t)1 << F) - 1) + (size_t)F;
+    if (lean) {
+      // only the bucket level (the new sets' finer levels are built on first use: an output of 0.2 M
+      // keys would otherwise cost 8 MB of offsets, 4 / 5 of everything this kernel writes)
+      if (tz == F) {
+        const size_t idx = x >> F;
+        if (l0) l0[idx] = pI;
+        if (l1) l1[idx] = pA;
+        if (l2) l2[idx] = pB;
+      }
+    } else
     for (int sh = 0; sh <= tz; sh++) {
       const size_t idx = start + (x >> sh);
       if (l0) l0[idx] = pI;
@@ -316,8 +330,8 @@ static int shell_alloc(kmsc_ctx* ctx, const kmsc_set* like, kmsc_set** out) {
 template <typename KeyT>
 static int launch_split(kmsc_ctx* ctx, const SplitPair* d_pairs, uint32_t total_units, uint32_t cpp, uint32_t NF, int N, int F,
                         int key_bits, int qlog, uint32_t xlo, uint32_t xhi, unsigned long long* d_state, uint32_t* d_ticket,
-                        uint32_t* d_totals) {
-  split_stream_kernel<KeyT><<<total_units, kSpThreads, 0, ctx->stream>>>(d_pairs, total_units / cpp, cpp, NF, N, F, key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals);
+                        uint32_t* d_totals, int lean) {
+  split_stream_kernel<KeyT><<<total_units, kSpThreads, 0, ctx->stream>>>(d_pairs, total_units / cpp, cpp, NF, N, F, key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals, lean);
   count_launch(ctx);
   KMSC_CUDA(cudaGetLastError());
   return KMSC_OK;
@@ -337,6 +351,11 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
   const kmsc_set* like = js[0];
   const int kb = like->key_bytes, N = like->N, F = like->max_level;
   const uint32_t NF = (uint32_t)1 << (N + F);
+  // the inputs are read at their finest level; the outputs get the bucket level only (lean) unless
+  // KMSC_SPLIT_LEVELS=full: their finer levels are built when a consumer first needs them
+  for (int32_t p = 0; p < m; p++) { KMSC_TRY(set_ensure_levels(ctx, js[p])); KMSC_TRY(set_ensure_levels(ctx, ks[p])); }
+  const char* lv_env = getenv("KMSC_SPLIT_LEVELS");
+  const int lean = (F > 0 && !(lv_env && strcmp(lv_env, "full") == 0)) ? 1 : 0;
   // threads per fine bucket: 2^qlog, so that a thread merges about 10 + 10 keys. The density is
   // taken over the bucket range the sets can hold keys in (a rank's prefix shard is N x denser)
   int qlog = 0;
@@ -392,6 +411,7 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
       SplitOut& o = ho[(size_t)p * 3 + q];
       rc = shell_alloc(ctx, like, &o.set);
       if (rc != KMSC_OK) break;
+      o.set->fine_ready = !lean;
       o.cap = (uint32_t)ub[q];
       o.direct = exact;
       P.lev[q] = o.set->lev_base;
@@ -442,9 +462,9 @@ static int split_run(kmsc_ctx* ctx, const kmsc_set* const* js, const kmsc_set* c
   if (e == cudaSuccess) e = cudaMemsetAsync(d_totals, 0, tot_b + 256 + state_b, ctx->stream);
   if (e != cudaSuccess) return fail(cuda_fail(e, "pair_split setup", __FILE__, __LINE__));
   switch (kb) {
-    case 2: rc = launch_split<uint16_t>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals); break;
-    case 4: rc = launch_split<uint32_t>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals); break;
-    default: rc = launch_split<unsigned long long>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals); break;
+    case 2: rc = launch_split<uint16_t>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals, lean); break;
+    case 4: rc = launch_split<uint32_t>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals, lean); break;
+    default: rc = launch_split<unsigned long long>(ctx, d_pairs, units, cpp, NF, N, F, like->key_bits, qlog, xlo, xhi, d_state, d_ticket, d_totals, lean); break;
   }
   if (rc != KMSC_OK) return fail(rc);
   uint32_t* h_tot = (uint32_t*)((char*)pin + std::max(desc_b, (size_t)m * 3 * sizeof(CopyDesc)));

@@ -17,8 +17,11 @@ int ceil_log2_u64(uint64_t x) {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t sort_smem_bytes(int FB2, uint32_t cap, int key_bytes) {
-  const size_t words = ((size_t)1 << FB2) + 1 + 33 + 1 + 2 * part::kLongCap;
-  return align_up(words * 4, 16) + 16 + align_up((size_t)cap * key_bytes, 16) + 16 + 2 * (((size_t)cap >> 5) + 2) * 4;
+  // cur | wsum | n_long | long_list | B | SB | dropw, dropp  (the offsets of sort_kernel)
+  size_t off = (((((size_t)1 << FB2) + 1 + 33 + 1 + 2 * part::kLongCap) * 4) + 15) & ~(size_t)15;
+  off = (off + ((size_t)cap + 4) * key_bytes + 15) & ~(size_t)15;
+  off = (off + (size_t)cap * 2 + 15) & ~(size_t)15;
+  return off + 2 * (((size_t)cap >> 5) + 2) * 4 + 16;
 }
 
 size_t partition_smem_bytes(int B1) {
@@ -136,7 +139,7 @@ int partition_plan(kmsc_ctx* ctx, const PipelineInput* in, int m, const Pipeline
     part_max = std::max(part_max, me[1]);
   }
   plan->part_max = part_max;
-  if (sort_smem_bytes(plan->FB2, part_max, opt.key_bytes) > 200 * 1024) return KMSC_OK;  // a partition too large for shared memory
+  if (part_max > 65535 || sort_smem_bytes(plan->FB2, part_max, opt.key_bytes) > 200 * 1024) return KMSC_OK;  // a partition too large for shared memory
   plan->feasible = true;
   return KMSC_OK;
 }

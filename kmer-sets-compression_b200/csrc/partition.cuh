@@ -32,7 +32,7 @@ constexpr int kThreads = 512;     // count / partition kernels
 constexpr int kSortThreads = 256; // sort kernel
 constexpr int kMaxB1 = 13;        // bins of the first level: at most 8192
 constexpr int kMaxSub = 13;       // sub-bins per partition: at most 8192
-constexpr int kLongRun = 32;      // sub-bin runs longer than this are sorted by the whole CTA
+constexpr int kLongRun = 24;      // sub-bin runs longer than this are sorted by the whole CTA
 constexpr int kLongCap = 512;     // such runs per partition (beyond: the owning thread heap-sorts)
 
 struct Job {
@@ -98,35 +98,83 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t* a, int n, uint32_t
   return total;
 }
 
-// k-mer starting at tile position i (global position p) out of the staged words
-__device__ __forceinline__ bool tile_kmer(const unsigned long long* sw, const uint32_t* sbad, uint32_t i,
-                                          unsigned long long p, unsigned long long n_pos, const Geo& g,
-                                          unsigned long long* out) {
-  if (p >= n_pos) return false;
-  if ((sbad[i >> 5] >> (i & 31)) & 1u) return false;
-  const uint32_t w = i >> 5;
-  const int o = (int)(i & 31) * 2;
-  unsigned long long x = sw[w] << o;
-  if (o) x |= sw[w + 1] >> (64 - o);
-  unsigned long long v = x >> (64 - g.V);
-  if (g.canonical) {
-    const unsigned long long rc = revcomp(v, g.K);
-    v = rc < v ? rc : v;
+// The kR = kTile / kThreads consecutive k-mers starting at tile position i0 (a multiple of kR),
+// rolled: the first window is cut out of the staged words, every further one shifts one base in
+// (forward strand) and its complement in from the other end (reverse strand), as the reference's
+// Kmer::Next does one k-mer at a time (lib/core/kmer.h:136-160); canonical = the smaller of the two
+// (kmer.h:133). emit(j, v) is called for every position that starts a k-mer kept by the bucket filter.
+constexpr int kR = kTile / kThreads;
+static_assert(kR == 16, "one 16-bit slice of the bad-position mask per thread");
+
+template <typename Emit>
+__device__ __forceinline__ void tile_kmers(const unsigned long long* sw, const uint32_t* sbad, uint32_t i0,
+                                           unsigned long long tile_base, unsigned long long n_pos, const Geo& g,
+                                           Emit&& emit) {
+  const unsigned long long p0 = tile_base + i0;
+  if (p0 >= n_pos) return;
+  uint32_t ok = ~(sbad[i0 >> 5] >> (i0 & 31)) & 0xffffu;
+  if (n_pos - p0 < (unsigned long long)kR) ok &= (1u << (uint32_t)(n_pos - p0)) - 1u;
+  if (!ok) return;
+  const unsigned long long mask = g.V >= 64 ? ~0ull : ((1ull << g.V) - 1);
+  unsigned long long fwd, rc;
+  {
+    const uint32_t w = i0 >> 5;
+    const int o = (int)(i0 & 31) * 2;
+    unsigned long long x = sw[w] << o;
+    if (o) x |= sw[w + 1] >> (64 - o);
+    fwd = x >> (64 - g.V);
+    rc = revcomp(fwd, g.K);
   }
-  const unsigned long long b = v >> g.key_bits;
-  if (b < g.bucket_lo || b >= g.bucket_hi) return false;
-  *out = v;
-  return true;
+  uint32_t next16;  // the 16 bases that follow the first window, first one in the top two bits
+  {
+    const uint32_t st = i0 + (uint32_t)g.K;
+    const uint32_t w = st >> 5;
+    const int o = (int)(st & 31) * 2;
+    unsigned long long x = sw[w] << o;
+    if (o) x |= sw[w + 1] >> (64 - o);
+    next16 = (uint32_t)(x >> 32);
+  }
+  const int top = g.V - 2;
+  const bool filter = g.bucket_lo != 0 || (g.bucket_hi >> (g.V - g.key_bits)) == 0;
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    if (ok & (1u << j)) {
+      const unsigned long long v = (g.canonical && rc < fwd) ? rc : fwd;
+      bool keep = true;
+      if (filter) {
+        const unsigned long long b = v >> g.key_bits;
+        keep = b >= g.bucket_lo && b < g.bucket_hi;
+      }
+      if (keep) emit(j, v);
+    }
+    const unsigned long long c = (next16 >> (30 - 2 * j)) & 3u;
+    fwd = ((fwd << 2) | c) & mask;
+    rc = (rc >> 2) | ((3ull - c) << top);
+  }
 }
 
-__device__ __forceinline__ void stage_tile(const Job& jb, unsigned long long tile_base, unsigned long long* sw,
-                                           uint32_t* sbad) {
+// A tile's packed words and bad-position mask travel through one register pair per thread
+// (kThreads >= kTile / 32 + 2): loaded one tile ahead, stored to shared memory when the tile's turn
+// comes, so the global-load latency hides behind the previous tile's work.
+struct TileRegs { unsigned long long w; uint32_t b; };
+static_assert(kThreads >= kTile / 32 + 2, "one staged word per thread");
+
+__device__ __forceinline__ TileRegs load_tile(const Job& jb, unsigned long long tile_base) {
   // the words array holds ceil(n_pos / 32) + 1 entries; positions past n_pos are never used
+  TileRegs t;
   const unsigned long long w0 = tile_base >> 5;
   const unsigned long long n_words = ((jb.n_pos + 31) >> 5) + 1;
-  for (int i = threadIdx.x; i < kTile / 32 + 1; i += blockDim.x) sw[i] = (w0 + i < n_words) ? jb.words[w0 + i] : 0ull;
   const unsigned long long n_badw = (jb.n_pos + 31) >> 5;
-  for (int i = threadIdx.x; i < kTile / 32; i += blockDim.x) sbad[i] = (w0 + i < n_badw) ? jb.bad[w0 + i] : 0xffffffffu;
+  const int i = threadIdx.x;
+  t.w = (i < kTile / 32 + 2 && tile_base < jb.n_pos && w0 + i < n_words) ? jb.words[w0 + i] : 0ull;
+  t.b = (i < kTile / 32 && tile_base < jb.n_pos && w0 + i < n_badw) ? jb.bad[w0 + i] : 0xffffffffu;
+  return t;
+}
+
+__device__ __forceinline__ void store_tile(const TileRegs& t, unsigned long long* sw, uint32_t* sbad) {
+  const int i = threadIdx.x;
+  if (i < kTile / 32 + 2) sw[i] = t.w;
+  if (i < kTile / 32) sbad[i] = t.b;
 }
 
 // ---- level 1, pass A: bin sizes per CTA ----------------------------------------------------------
@@ -139,16 +187,14 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const Job* __restrict__
   uint32_t* hist = sbad + kTile / 32;                       // bins
   for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[i] = 0;
   const unsigned long long n_tiles = (jb.n_pos + kTile - 1) / kTile;
+  TileRegs nxt = load_tile(jb, (unsigned long long)blockIdx.x * kTile);
   for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     __syncthreads();
-    stage_tile(jb, t * kTile, sw, sbad);
+    store_tile(nxt, sw, sbad);
+    nxt = load_tile(jb, (t + gridDim.x) * kTile);
     __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < kTile / kThreads; r++) {
-      const uint32_t i = r * kThreads + threadIdx.x;
-      unsigned long long v;
-      if (tile_kmer(sw, sbad, i, t * kTile + i, jb.n_pos, g, &v)) atomicAdd(&hist[(uint32_t)(v >> g.R1)], 1u);
-    }
+    tile_kmers(sw, sbad, threadIdx.x * kR, t * kTile, jb.n_pos, g,
+               [&](int, unsigned long long v) { atomicAdd(&hist[(uint32_t)(v >> g.R1)], 1u); });
   }
   __syncthreads();
   uint32_t* mine = jb.slice + (size_t)blockIdx.x * bins;
@@ -167,10 +213,18 @@ __global__ void __launch_bounds__(1024) scan_kernel(const Job* __restrict__ jobs
   uint32_t m = 0;
   for (int i = threadIdx.x; i < bins; i += blockDim.x) {
     uint32_t run = 0;
-    for (int c = 0; c < n_ctas; c++) {   // coalesced over the threads; the loads of different c are independent
-      uint32_t* p = jb.slice + (size_t)c * bins + i;
-      const uint32_t v = *p;
-      *p = run;                          // offset of CTA c's slice inside the bin
+    uint32_t* col = jb.slice + i;        // coalesced over the threads
+    int c = 0;
+    for (; c + 8 <= n_ctas; c += 8) {    // eight independent loads in flight, then the running offsets
+      uint32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = col[(size_t)(c + u) * bins];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { col[(size_t)(c + u) * bins] = run; run += v[u]; }
+    }
+    for (; c < n_ctas; c++) {
+      const uint32_t v = col[(size_t)c * bins];
+      col[(size_t)c * bins] = run;       // offset of CTA c's slice inside the bin
       run += v;
     }
     a[i] = run;
@@ -185,7 +239,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const Job* __restrict__ jobs
 
 // ---- level 1, pass B: group every tile by bin in shared memory, write contiguous runs -------------
 template <typename TmpT>
-__global__ void __launch_bounds__(kThreads) partition_kernel(const Job* __restrict__ jobs, Geo g) {
+__global__ void __launch_bounds__(kThreads, 2) partition_kernel(const Job* __restrict__ jobs, Geo g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Job jb = jobs[blockIdx.y];
   const int bins = 1 << g.B1;
@@ -204,23 +258,21 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(const Job* __restri
   const unsigned long long rmask = g.R1 >= 64 ? ~0ull : ((1ull << g.R1) - 1);
   const unsigned long long n_tiles = (jb.n_pos + kTile - 1) / kTile;
   constexpr int R = kTile / kThreads;
+  TileRegs nxt = load_tile(jb, (unsigned long long)blockIdx.x * kTile);
   for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const unsigned long long tile_base = t * kTile;
     __syncthreads();   // the previous tile's write-out has finished reading sorted / gadj
     for (int i = threadIdx.x; i <= bins; i += blockDim.x) lcur[i] = 0;
-    stage_tile(jb, tile_base, sw, sbad);
+    store_tile(nxt, sw, sbad);
+    nxt = load_tile(jb, (t + gridDim.x) * kTile);
     __syncthreads();
     unsigned long long v[R];
     uint32_t valid = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const uint32_t i = r * kThreads + threadIdx.x;
-      v[r] = 0;
-      if (tile_kmer(sw, sbad, i, tile_base + i, jb.n_pos, g, &v[r])) {
-        valid |= 1u << r;
-        atomicAdd(&lcur[(uint32_t)(v[r] >> g.R1)], 1u);
-      }
-    }
+    tile_kmers(sw, sbad, threadIdx.x * kR, tile_base, jb.n_pos, g, [&](int j, unsigned long long x) {
+      v[j] = x;
+      valid |= 1u << j;
+      atomicAdd(&lcur[(uint32_t)(x >> g.R1)], 1u);
+    });
     __syncthreads();
     const uint32_t n_valid = block_excl_scan(lcur, bins, wsum);
     for (int i = threadIdx.x; i < bins; i += blockDim.x) gadj[i] = gcur[i] - lcur[i];
@@ -239,17 +291,6 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(const Job* __restri
 }
 
 // ---- level 2: one CTA per partition ----------------------------------------------------------------
-template <typename KeyT>
-__device__ __forceinline__ void insertion_sort(KeyT* a, uint32_t L, bool* dup) {
-  for (uint32_t i = 1; i < L; i++) {
-    const KeyT x = a[i];
-    uint32_t j = i;
-    while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; }
-    a[j] = x;
-    if (j > 0 && a[j - 1] == x) *dup = true;
-  }
-}
-
 template <typename KeyT>
 __device__ void heap_sort(KeyT* a, uint32_t L) {
   auto sift = [&](uint32_t start, uint32_t end) {
@@ -273,11 +314,18 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const Job* __restric
   const uint32_t base = jb.base[bin];
   const uint32_t P = jb.base[bin + 1] - base;
   const int nsub = 1 << g.FB2;
-  uint32_t* cur = (uint32_t*)smem_raw;                 // nsub + 1: counts -> exclusive starts -> run ends
-  uint32_t* wsum = cur + nsub + 1;                     // 33
-  uint32_t* n_long = wsum + 33;                        // 1
-  uint32_t* long_list = n_long + 1;                    // 2 * kLongCap
-  KeyT* B = (KeyT*)(((uintptr_t)(long_list + 2 * kLongCap) + 15) & ~(uintptr_t)15);  // cap keys
+  // shared memory (offsets, so that every access stays in the shared address space):
+  //   cur[nsub + 1] | wsum[33] | n_long | long_list[2 kLongCap] | B[cap] keys by slot | SB[cap] sub-bin of the slot
+  //   | dropw, dropp (dedup only)
+  uint32_t* cur = (uint32_t*)smem_raw;                 // counts -> exclusive starts -> run ends
+  uint32_t* wsum = cur + nsub + 1;
+  uint32_t* n_long = wsum + 33;
+  uint32_t* long_list = n_long + 1;
+  const uint32_t off_b = (uint32_t)(((nsub + 1 + 33 + 1 + 2 * kLongCap) * 4 + 15) & ~15);
+  KeyT* B = (KeyT*)(smem_raw + off_b);
+  const uint32_t off_sb = (off_b + (cap + 4) * (uint32_t)sizeof(KeyT) + 15u) & ~15u;
+  uint16_t* SB = (uint16_t*)(smem_raw + off_sb);
+  const uint32_t off_drop = (off_sb + cap * 2u + 15u) & ~15u;
   const TmpT* tmp = (const TmpT*)jb.tmp + base;
   const int sub_shift = g.R1 - g.FB2;
   if (P > cap) {  // cannot happen: the host sizes cap from the largest partition
@@ -287,7 +335,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const Job* __restric
   for (int i = threadIdx.x; i <= nsub; i += blockDim.x) cur[i] = 0;
   if (threadIdx.x == 0) *n_long = 0;
   __syncthreads();
-  // four independent loads in flight per thread
+  // pass 1: sub-bin sizes; four independent loads in flight per thread
   for (uint32_t i0 = threadIdx.x; i0 < P; i0 += 4 * kSortThreads) {
     TmpT r[4];
 #pragma unroll
@@ -308,9 +356,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const Job* __restric
     if (bin == (uint32_t)bins - 1 && threadIdx.x == 0) fine[nfine] = base + P;
   }
   __syncthreads();
+  // pass 2: every key takes a slot of its sub-bin (second read: L1 / L2 hits)
   const unsigned long long kmask = g.key_bits >= 64 ? ~0ull : ((1ull << g.key_bits) - 1);
   const unsigned long long hi_part = g.R1 >= 64 ? 0ull : ((unsigned long long)bin << g.R1);
-  for (uint32_t i0 = threadIdx.x; i0 < P; i0 += 4 * kSortThreads) {  // second read: L1 / L2 hits
+  for (uint32_t i0 = threadIdx.x; i0 < P; i0 += 4 * kSortThreads) {
     TmpT r[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) { const uint32_t i = i0 + u * kSortThreads; r[u] = i < P ? tmp[i] : (TmpT)0; }
@@ -318,70 +367,129 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const Job* __restric
     for (int u = 0; u < 4; u++)
       if (i0 + u * kSortThreads < P) {
         const unsigned long long x = (unsigned long long)r[u];
-        const uint32_t pos = atomicAdd(&cur[(uint32_t)(x >> sub_shift)], 1u);
-        B[pos] = (KeyT)((hi_part | x) & kmask);
+        const uint32_t sb = (uint32_t)(x >> sub_shift);
+        const uint32_t slot = atomicAdd(&cur[sb], 1u);
+        B[slot] = (KeyT)((hi_part | x) & kmask);
+        SB[slot] = (uint16_t)sb;
       }
   }
   __syncthreads();
-  // cur[s] is now the END of sub-bin s; its start is cur[s - 1]
-  bool dup = false;
-  for (int s = threadIdx.x; s < nsub; s += blockDim.x) {
-    const uint32_t a = s ? cur[s - 1] : 0u, L = cur[s] - a;
-    if (L < 2) continue;
-    if (L <= (uint32_t)kLongRun) {
-      insertion_sort(B + a, L, &dup);
-    } else {
-      const uint32_t slot = atomicAdd(n_long, 1u);
-      if (slot < (uint32_t)kLongCap) {
-        long_list[2 * slot] = a;
-        long_list[2 * slot + 1] = L;
-      } else {
-        heap_sort(B + a, L);
-        for (uint32_t i = 1; i < L; i++) dup |= B[a + i] == B[a + i - 1];
-      }
-    }
-  }
-  __syncthreads();
-  // long runs (repeated k-mers, low-complexity sequence): the whole CTA sorts each with a
-  // bitonic network whose merges all run ascending, so the virtual +inf padding never moves
-  const uint32_t nl = min(*n_long, (uint32_t)kLongCap);
-  for (uint32_t q = 0; q < nl; q++) {
-    const uint32_t a = long_list[2 * q], L = long_list[2 * q + 1];
-    uint32_t Pw = 1;
-    while (Pw < L) Pw <<= 1;
-    for (uint32_t k = 2; k <= Pw; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < Pw; i += blockDim.x) {
-          const uint32_t l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
-          if (l > i && l < L) {
-            const KeyT x = B[a + i], y = B[a + l];
-            if (x > y) { B[a + i] = y; B[a + l] = x; }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    for (uint32_t i = threadIdx.x + 1; i < L; i += blockDim.x) dup |= B[a + i] == B[a + i - 1];
-  }
-  const int any_dup = __syncthreads_or(dup ? 1 : 0);
-  if (any_dup && threadIdx.x == 0) atomicOr(&jb.meta[2], 1u);
+  // cur[s] is now the END of sub-bin s; its start is cur[s - 1]. A sub-bin holds about one key:
+  // every key finds its rank among the keys of its sub-bin (equal keys: slot order) and goes
+  // straight to its place in the result. Runs too long for that are left to the whole CTA.
   KeyT* out = (KeyT*)jb.keys + base;
-  if (!(any_dup && g.dedup)) {
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) out[i] = B[i];
-    return;
+  int dup = 0;
+  for (uint32_t slot = threadIdx.x; slot < P; slot += blockDim.x) {
+    const KeyT key = B[slot];
+    const uint32_t sb = SB[slot];
+    const uint32_t a = sb ? cur[sb - 1] : 0u, e = cur[sb];
+    if (e - a > (uint32_t)kLongRun) {
+      if (slot == a) {
+        const uint32_t q = atomicAdd(n_long, 1u);
+        if (q < (uint32_t)kLongCap) { long_list[2 * q] = a; long_list[2 * q + 1] = e - a; }
+      }
+      continue;
+    }
+    // the first four slots of the run without a loop (a sub-bin holds about one key; B has four
+    // spare entries past cap); equal keys are rare and settled by slot order afterwards
+    const uint32_t L = e - a;
+    uint32_t lt = 0, eq = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < 4; t++) {
+      const KeyT x = B[a + t];
+      const bool in = t < L;
+      lt += (in && x < key) ? 1u : 0u;
+      eq += (in && x == key) ? 1u : 0u;
+    }
+    for (uint32_t j = a + 4; j < e; j++) {
+      const KeyT x = B[j];
+      lt += x < key ? 1u : 0u;
+      eq += x == key ? 1u : 0u;
+    }
+    if (eq > 1) {
+      dup = 1;
+      for (uint32_t j = a; j < slot; j++) lt += B[j] == key ? 1u : 0u;
+    }
+    out[a + lt] = key;
   }
-  // rare: this partition holds a key more than once and the caller wants a set. Mark the copies,
-  // write the survivors packed from the partition's base and re-derive its fine offsets; the
+  __syncthreads();
+  // long runs (repeated k-mers, low-complexity sequence): the whole CTA sorts each in place with
+  // a bitonic network whose merges all run ascending, so the virtual +inf padding never moves;
+  // past kLongCap of them, one thread heap-sorts each of the rest
+  const uint32_t n_l = *n_long;
+  if (n_l) {
+    const uint32_t nl = min(n_l, (uint32_t)kLongCap);
+    for (uint32_t q = 0; q < nl; q++) {
+      const uint32_t a = long_list[2 * q], L = long_list[2 * q + 1];
+      uint32_t Pw = 1;
+      while (Pw < L) Pw <<= 1;
+      for (uint32_t k = 2; k <= Pw; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t i = threadIdx.x; i < Pw; i += blockDim.x) {
+            const uint32_t l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+            if (l > i && l < L) {
+              const KeyT x = B[a + i], y = B[a + l];
+              if (x > y) { B[a + i] = y; B[a + l] = x; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
+        out[a + i] = B[a + i];
+        if (i > 0) dup |= B[a + i] == B[a + i - 1];
+      }
+    }
+    if (n_l > (uint32_t)kLongCap) {
+      // the listed ones are done; find the unlisted long runs again (their first slot) and sort them serially
+      for (int sb = threadIdx.x; sb < nsub; sb += blockDim.x) {
+        const uint32_t a = sb ? cur[sb - 1] : 0u, L = cur[sb] - a;
+        if (L <= (uint32_t)kLongRun) continue;
+        bool listed = false;
+        for (uint32_t q = 0; q < nl && !listed; q++) listed = long_list[2 * q] == a;
+        if (listed) continue;
+        heap_sort(B + a, L);
+        for (uint32_t i = 0; i < L; i++) {
+          out[a + i] = B[a + i];
+          if (i > 0) dup |= B[a + i] == B[a + i - 1];
+        }
+      }
+    }
+  }
+  const int any_dup = __syncthreads_or(dup);
+  if (any_dup && threadIdx.x == 0) atomicOr(&jb.meta[2], 1u);
+  if (!(any_dup && g.dedup)) return;
+  // rare: this partition holds a key more than once and the caller wants a set. Every key finds
+  // its place again; copies (an equal key in an earlier slot) are marked at their place, the
+  // survivors are written packed from the partition's base and the fine offsets re-derived; the
   // gaps between partitions are closed by shift_kernel once every partition's count is known.
-  uint32_t* dropw = (uint32_t*)(((uintptr_t)(B + cap) + 15) & ~(uintptr_t)15);  // cap / 32 + 1 mask words
-  uint32_t* dropp = dropw + (cap >> 5) + 2;                                      // their exclusive popcount prefix
+  uint32_t* dropw = (uint32_t*)(smem_raw + off_drop);   // cap / 32 + 2 mask words over the sorted places
+  uint32_t* dropp = dropw + (cap >> 5) + 2;             // their exclusive popcount prefix
   const int nwords = (int)(P >> 5) + 1;
   for (int w = threadIdx.x; w < nwords; w += blockDim.x) dropw[w] = 0;
   __syncthreads();
-  for (int sb = threadIdx.x; sb < nsub; sb += blockDim.x) {
+  auto place_of = [&](uint32_t slot, bool* copy) {   // long runs are sorted in place: slot order = key order
+    const KeyT key = B[slot];
+    const uint32_t sb = SB[slot];
     const uint32_t a = sb ? cur[sb - 1] : 0u, e = cur[sb];
-    for (uint32_t i = a + 1; i < e; i++)
-      if (B[i] == B[i - 1]) atomicOr(&dropw[i >> 5], 1u << (i & 31));
+    if (e - a > (uint32_t)kLongRun) {
+      *copy = slot > a && B[slot - 1] == key;
+      return slot;
+    }
+    uint32_t rank = 0;
+    bool c = false;
+    for (uint32_t j = a; j < e; j++) {
+      const KeyT x = B[j];
+      rank += (x < key) || (x == key && j < slot);
+      c |= (x == key) && (j < slot);
+    }
+    *copy = c;
+    return a + rank;
+  };
+  for (uint32_t slot = threadIdx.x; slot < P; slot += blockDim.x) {
+    bool copy;
+    const uint32_t q = place_of(slot, &copy);
+    if (copy) atomicOr(&dropw[q >> 5], 1u << (q & 31));
   }
   __syncthreads();
   for (int w = threadIdx.x; w < nwords; w += blockDim.x) dropp[w] = __popc(dropw[w]);
@@ -399,8 +507,11 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(const Job* __restric
     }
     if (bin == (uint32_t)bins - 1 && threadIdx.x == 0) fine[nfine] = base + P - removed;
   }
-  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
-    if (!((dropw[i >> 5] >> (i & 31)) & 1u)) out[new_index(i)] = B[i];
+  for (uint32_t slot = threadIdx.x; slot < P; slot += blockDim.x) {
+    bool copy;
+    const uint32_t q = place_of(slot, &copy);
+    if (!copy) out[new_index(q)] = B[slot];
+  }
   if (threadIdx.x == 0) {
     jb.removed[bin] = removed;
     atomicAdd(&jb.meta[3], removed);

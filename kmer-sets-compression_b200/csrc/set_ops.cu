@@ -256,6 +256,8 @@ static int counted_union_t(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, 
 int counted_union(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kmsc_set* b, const uint8_t* cb,
                   kmsc_set** out, uint8_t** out_counts) {
   KMSC_TRY(check_pair(a, b));
+  KMSC_TRY(set_ensure_levels(ctx, a));
+  KMSC_TRY(set_ensure_levels(ctx, b));
   switch (a->key_bytes) {
     case 2: return counted_union_t<uint16_t>(ctx, a, ca, b, cb, out, out_counts);
     case 4: return counted_union_t<uint32_t>(ctx, a, ca, b, cb, out, out_counts);
@@ -285,6 +287,8 @@ int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_s
     const kmsc_set* a = acc ? acc : sets[0];
     if (t == 0 && m > 1) continue;
     int rc = check_pair(a, b);
+    if (rc == KMSC_OK) rc = set_ensure_levels(ctx, a);
+    if (rc == KMSC_OK) rc = set_ensure_levels(ctx, b);
     MergePlan mp;
     uint32_t tot[3];
     if (rc == KMSC_OK) rc = merge_count(ctx, a, b, &mp, true, tot);

@@ -30,7 +30,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.kmsc_pair_counts_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.kmsc_pair_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i64p, _i64p]
     L.kmsc_pair_counts_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, C.c_void_p]
+    L.kmsc_pair_counts_partial.argtypes = L.kmsc_pair_counts_device.argtypes
     L.kmsc_pair_counts_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.c_int32, _i32p,
                                         C.c_int32, _i64p]
     L.kmsc_pair_counts_build.argtypes = [C.c_void_p]
@@ -108,6 +109,11 @@ def lib() -> C.CDLL:
     L.kmsc_set_export_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.kmsc_set_import_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.POINTER(C.c_void_p)]
+    L.kmsc_comm_unique_id.argtypes = [C.c_void_p]
+    L.kmsc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.kmsc_comm_destroy.argtypes = [C.c_void_p]
+    L.kmsc_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.kmsc_sets_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.POINTER(C.c_void_p), C.c_int32]
     L.kmsc_counter_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.kmsc_counter_add_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
     L.kmsc_counter_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
@@ -279,14 +285,16 @@ class Context:
         _check(lib().kmsc_pair_counts(self.h, self._handles(sets), n, idp, nid, out.ctypes.data_as(_i64p), C.byref(visits)))
         return (out, visits.value) if with_visits else out
 
-    def pair_counts_device(self, sets, d_out_ptr: int, bucket_ids=None):
+    def pair_counts_device(self, sets, d_out_ptr: int, bucket_ids=None, partial=False):
+        """matrix left on the device; partial=True: this rank's own counts, no all-reduce"""
         n = len(sets)
         if bucket_ids is None:
             idp, nid = None, 0
         else:
             ids = np.ascontiguousarray(bucket_ids, np.int32)
             idp, nid = ids.ctypes.data_as(_i32p), len(ids)
-        _check(lib().kmsc_pair_counts_device(self.h, self._handles(sets), n, idp, nid, C.c_void_p(d_out_ptr)))
+        fn = lib().kmsc_pair_counts_partial if partial else lib().kmsc_pair_counts_device
+        _check(fn(self.h, self._handles(sets), n, idp, nid, C.c_void_p(d_out_ptr)))
 
     def pair_counts_build(self) -> int:
         """0 = hash build, 1 = merge build (main phase of the last pair_counts call)"""
@@ -310,6 +318,32 @@ class Context:
         out = np.zeros((max(1, s.n_keys), 8), np.int32)
         _check(lib().kmsc_set_neighbors(self.h, s.h, int(canonical), out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out[: s.n_keys]
+
+    # -- multi-GPU inside the library -----------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().kmsc_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, n_ranks: int, id128: bytes):
+        assert len(id128) == 128
+        _check(lib().kmsc_comm_init(self.h, rank, n_ranks, C.c_char_p(id128)))
+
+    def comm_destroy(self):
+        _check(lib().kmsc_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, n = C.c_int(), C.c_int()
+        _check(lib().kmsc_comm_info(self.h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def sets_exchange(self, mine, cuts, n_total):
+        """whole sets decoded by this rank -> all n_total sets restricted to this rank's bucket range"""
+        cuts = np.ascontiguousarray(cuts, np.int32)
+        out = (C.c_void_p * n_total)()
+        _check(lib().kmsc_sets_exchange(self.h, self._handles(mine) if mine else None, len(mine), cuts.ctypes.data_as(_i32p), out, n_total))
+        return [DeviceSet(self, out[g]) for g in range(n_total)]
 
     # -- multi-GPU exchange helpers ---------------------------------------------------------
     def set_bucket_offsets(self, s: DeviceSet, buckets) -> np.ndarray:

@@ -660,6 +660,24 @@ void kmsc_o_dsu_unite(kmsc_o_dsu* d, int32_t x, int32_t y) {
   if (rx == ry) d->a[y] = ((uint64_t)(ry + 1) << 32) + (uint64_t)y; /* rank bump, :73-75 */
 }
 
+/* k-mer positions per bucket (duplicates counted) of 2-bit codes 0..3: the bucket sizes
+ * GetSampledKmerSet would produce (kmer_set_compact.h:145-163), without building the sets.
+ * Used by bench.py to state the key-visits of a reference run. hist: 2^N entries, added to. */
+void kmsc_o_bucket_histogram(const uint8_t* codes, int64_t n, int K, int N, int canonical, int64_t* hist) {
+  if (n < K) return;
+  const uint64_t mask = K == 32 ? ~(uint64_t)0 : (((uint64_t)1 << (2 * K)) - 1);
+  uint64_t fwd = 0, rc = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const uint64_t c = codes[i] & 3u;
+    fwd = ((fwd << 2) | c) & mask;
+    rc = (rc >> 2) | ((3 - c) << (2 * (K - 1)));
+    if (i >= K - 1) {
+      const uint64_t v = (canonical && rc < fwd) ? rc : fwd;
+      hist[v >> (2 * K - N)]++;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------- */
 /* `mst` driver (north_star variant; the snapshot has no counterpart) */
 /* ------------------------------------------------------------------------- */

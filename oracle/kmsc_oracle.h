@@ -128,6 +128,10 @@ int32_t  kmsc_o_dsu_find(kmsc_o_dsu*, int32_t x);            /* :24-40 */
 int      kmsc_o_dsu_same(kmsc_o_dsu*, int32_t x, int32_t y); /* :43-50 */
 void     kmsc_o_dsu_unite(kmsc_o_dsu*, int32_t x, int32_t y);/* :53-78 */
 
+/* bucket sizes of GetSampledKmerSet over all buckets (kmer_set_compact.h:145-163) for a sequence
+ * given as codes 0..3, without building the sets: hist[2^N] += k-mer positions per bucket. */
+void     kmsc_o_bucket_histogram(const uint8_t* codes, int64_t n, int K, int N, int canonical, int64_t* hist);
+
 /* ---- `mst` driver (north_star; no counterpart in the snapshot: SURVEY.md App. C) ---------- */
 /* w = exact n x n intersection matrix with the set sizes on the diagonal. Kruskal over
  * d(i,j) = |S_i| + |S_j| - 2 w[i][j], candidates ordered by (d, i, j), union-find as

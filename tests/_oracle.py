@@ -103,6 +103,8 @@ class Oracle:
         L.kmsc_o_greedy_should_stop.argtypes = [C.c_int64, C.c_int64, C.c_int32]
         L.kmsc_o_greedy_argmax.argtypes = [i64p, C.c_int32, i32p, i32p]
         L.kmsc_o_greedy_argmax.restype = C.c_int64
+        L.kmsc_o_bucket_histogram.argtypes = [u8p, C.c_int64, C.c_int, C.c_int, C.c_int, i64p]
+        L.kmsc_o_bucket_histogram.restype = None
         L.kmsc_o_mst.argtypes = [i64p, C.c_int32, i32p, i64p]
         L.kmsc_o_mst.restype = C.c_int32
         L.kmsc_o_dsu_new.argtypes = [C.c_int32]
@@ -286,6 +288,12 @@ class Oracle:
         j, k = C.c_int32(), C.c_int32()
         v = self.lib.kmsc_o_greedy_argmax(_ptr(w, i64p), w.shape[0], C.byref(j), C.byref(k))
         return v, j.value, k.value
+
+    def bucket_histogram(self, codes, K, N, canonical=True):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        hist = np.zeros(1 << N, np.int64)
+        self.lib.kmsc_o_bucket_histogram(_ptr(codes, u8p), len(codes), K, N, int(canonical), _ptr(hist, i64p))
+        return hist
 
     def mst(self, w):
         """(edges [(parent, child)], distances) of the `mst` driver over an exact intersection matrix"""

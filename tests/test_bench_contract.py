@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--ref-sets", "2", "--kmers", "100000"], capture_output=True, text=True, timeout=600)
+                        "--sets", "6", "--kmers", "100000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -21,6 +21,11 @@ def test_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # the arm says what it measured, and measures both of the reference's modes on all the sets
+    assert "reference_sample" in d["config"] and d["config"]["n_sets"] == 6
+    assert d["phases"]["pair_rate"] > 0 and d["phases"]["t_decode_wave_s"] > 0
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert d["sampled"]["n_sets"] == 6 and d["sampled"]["value"] > 0
 
 
 def test_our_arm_fails_loudly_without_a_gpu():

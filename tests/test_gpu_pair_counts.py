@@ -125,8 +125,8 @@ def test_skewed_single_bucket(ctx, oracle):
 def test_all_ones_key(ctx, oracle):
     """key == 0xFFFFFFFF (valid when 2K-N == 32) must not be taken for the empty marker"""
     K, N, kb = 23, 14, 4
-    a = np.array([0xFFFFFFFF, (5 << 32) | 0xFFFFFFFF, (5 << 32) | 7, (1 << 46) - 1], np.uint64)
-    b = np.array([0xFFFFFFFF, (5 << 32) | 0xFFFFFFFF, (5 << 32) | 8, (1 << 46) - 1], np.uint64)
+    a = np.sort(np.array([0xFFFFFFFF, (5 << 32) | 0xFFFFFFFF, (5 << 32) | 7, (1 << 46) - 1], np.uint64))
+    b = np.sort(np.array([0xFFFFFFFF, (5 << 32) | 0xFFFFFFFF, (5 << 32) | 8, (1 << 46) - 1], np.uint64))
     c = np.array([1, (5 << 32) | 0xFFFFFFFE], np.uint64)
     got = _check(ctx, oracle, [a, b, c], K, N, kb)
     assert got[0, 1] == 3 and got[0, 2] == 0
@@ -151,15 +151,60 @@ def test_duplicate_keys_multiset(ctx, oracle):
     assert got[0, 1] == want[0, 1] == 4
 
 
-def test_rows_mode(ctx, oracle):
+def _oracle_rows(oracle, offs_l, keys_l, rows, kb, n_buckets, bucket_ids=None):
+    """rows of the reference's weight matrix, pair by pair (GetEdgeWeight, kmer_set_set.h:158-184)"""
+    n = len(offs_l)
+    out = np.zeros((len(rows), n), np.int64)
+    for a, r in enumerate(rows):
+        for l in range(n):
+            w, _ = oracle.pair_counts([offs_l[r], offs_l[l]], [keys_l[r], keys_l[l]], kb, n_buckets, bucket_ids=bucket_ids)
+            out[a, l] = w[0, 1]
+    return out
+
+
+@pytest.mark.parametrize("K,N,kb", [(23, 14, 4), (15, 14, 2), (31, 14, 8), (19, 10, 4)])
+def test_rows_mode_vs_oracle(ctx, oracle, K, N, kb):
+    """row mode = the 3n-2 re-weights after a merge (kmer_set_set.h:385-425), against the oracle's own
+    merge counts (not against the product's full matrix): all buckets and a sampled bucket list"""
     import synth
-    K, N, kb = 23, 14, 4
-    seqs = synth.phylogeny_sequences(9, 20000, p=0.01, seed=3)
+    seqs = synth.phylogeny_sequences(9, 20000, p=0.01, seed=3 + K)
     sets = [synth.kmer_set_of(s, K) for s in seqs]
+    sets[4] = sets[4][:50]                      # a tiny set
+    sets[6] = np.zeros(0, np.uint64)            # an empty one
     dev, offs_l, keys_l = _mk_sets(ctx, oracle, sets, K, N, kb)
-    full = ctx.pair_counts(dev)
-    rows = ctx.pair_counts_rows(dev, [2, 5, 8])
-    assert np.array_equal(rows, full[[2, 5, 8]])
+    rows = [2, 5, 8]
+    got = ctx.pair_counts_rows(dev, rows)
+    want = _oracle_rows(oracle, offs_l, keys_l, rows, kb, 1 << N)
+    assert np.array_equal(got, want)
+    ids = np.random.default_rng(1).choice(1 << N, max(4, (1 << N) // 50), replace=False).astype(np.int32)
+    ids = np.concatenate([ids, ids[:3]])        # an id listed twice counts once
+    got = ctx.pair_counts_rows(dev, rows, bucket_ids=ids)
+    want = _oracle_rows(oracle, offs_l, keys_l, rows, kb, 1 << N, bucket_ids=np.unique(ids))
+    assert np.array_equal(got, want)
+    # more rows than one launch takes, a row listed twice, a row against itself
+    rows = [0, 1, 2, 3, 4, 5, 6, 7, 8, 3]
+    got = ctx.pair_counts_rows(dev, rows)
+    assert np.array_equal(got, _oracle_rows(oracle, offs_l, keys_l, rows, kb, 1 << N))
+
+
+def test_rows_mode_dense_and_duplicates(ctx, oracle):
+    """runs far longer than the staging tile (one bucket holds everything) and multiset inputs:
+    the merge counts min multiplicity like the reference's loop"""
+    K, N, kb = 23, 14, 4
+    rng = np.random.default_rng(5)
+    base = (np.uint64(77) << np.uint64(32)) | np.unique(rng.integers(0, 1 << 20, 30000).astype(np.uint64))
+    a = base[rng.random(len(base)) < 0.7]
+    b = base[rng.random(len(base)) < 0.7]
+    c = np.sort(np.concatenate([a[:2000], a[:2000], b[:10]]))   # duplicates
+    dev, offs_l, keys_l = [], [], []
+    import synth
+    for km in (a, b, c):
+        offs, keys = synth.csr_of(km, K, N, kb)
+        dev.append(ctx.set_from_csr(K, N, kb, offs, keys))
+        offs_l.append(offs)
+        keys_l.append(keys)
+    got = ctx.pair_counts_rows(dev, [0, 2])
+    assert np.array_equal(got, _oracle_rows(oracle, offs_l, keys_l, [0, 2], kb, 1 << N))
 
 
 def test_set_roundtrip_size_hash(ctx, oracle):

@@ -339,3 +339,36 @@ def test_neighbor_table(ctx, oracle, K, N, canonical):
                     flip = int(q != w)
                 want = (index[q] << 1 | flip) if q in index else -1
                 assert nb[i, d + c] == want, (i, d, c)
+
+
+def test_set_from_csr_rejects_bad_input(ctx):
+    """unsorted keys, keys wider than 2K-N bits and impossible shapes are refused instead of
+    producing wrong matrices later; K = 32 with N = 0 (64 key bits) is not supported"""
+    import kmsc
+    K, N = 23, 14
+    offs = np.zeros((1 << N) + 1, np.int64)
+    offs[6:] = 2
+    with pytest.raises(kmsc.KmscError):
+        ctx.set_from_csr(K, N, 4, offs, np.array([9, 3], np.uint32))           # descending inside bucket 5
+    assert ctx.set_from_csr(K, N, 4, offs, np.array([3, 9], np.uint32)).Size() == 2
+    with pytest.raises(kmsc.KmscError):
+        ctx.set_from_csr(15, 14, 4, offs, np.array([3, 1 << 20], np.uint32))  # 2K-N = 16 bits
+    with pytest.raises(kmsc.KmscError):
+        ctx.set_from_csr(32, 0, 8, np.array([0, 1], np.int64), np.array([5], np.uint64))
+    with pytest.raises(kmsc.KmscError):
+        ctx.set_from_csr(23, 40, 4, offs, np.array([3, 9], np.uint32))
+
+
+def test_split_and_union_refuse_multisets(ctx):
+    """split / diff / union assume true sets; a set holding a key twice is refused"""
+    import kmsc
+    K, N = 23, 14
+    offs = np.zeros((1 << N) + 1, np.int64)
+    offs[1:] = 3
+    multi = ctx.set_from_csr(K, N, 4, offs, np.array([4, 4, 9], np.uint32))
+    plain = ctx.set_from_csr(K, N, 4, offs, np.array([4, 5, 9], np.uint32))
+    for call in (lambda: ctx.pair_split(multi, plain), lambda: ctx.pair_split(plain, multi),
+                 lambda: ctx.set_diff(multi, plain), lambda: ctx.set_union([plain, multi])):
+        with pytest.raises(kmsc.KmscError):
+            call()
+    assert ctx.set_union([plain, plain]).Size() == 3
