@@ -61,9 +61,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C2", "C3"],
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"],
                     help="C2 (BASELINE configs[1], the metric's config): 64 sets x 10M 23-mers per GPU, weak scaling; "
-                         "C3 (configs[2]): 256 sets x 10M 23-mers in all, prefix-sharded over the GPUs, strong scaling")
+                         "C3 (configs[2]): 256 sets x 10M 23-mers in all, prefix-sharded over the GPUs, strong scaling; "
+                         "C4 (configs[3]): k-mer counting of synthetic FASTA reads, k=31, cutoff 4 (--bytes, default 2 GB slice); "
+                         "C5 (configs[4]): k=15 dense-bitmap AND-popcount Gram of 512 sets (one GPU)")
+    ap.add_argument("--bytes", type=int, default=2_000_000_000, help="C4: bytes of FASTA to count")
+    ap.add_argument("--chunk-bytes", type=int, default=256_000_000, help="C4: bytes per streamed chunk")
     ap.add_argument("--sets", type=int, default=0, help="number of sets (default: 64 for C2, 256 for C3)")
     ap.add_argument("--kmers", type=int, default=10_000_000, help="k-mers per set (C2: per GPU)")
     ap.add_argument("--p", type=float, default=0.002)
@@ -71,7 +75,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stage", action="store_true")
+    ap.add_argument("--profile-e2e", action="store_true", help="diagnostic: per-phase times of the e2e step on stderr (synchronises between phases)")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle check of W at full size")
+    ap.add_argument("--no-c1", action="store_true", help="skip the bounded C1 end-to-end run of the executable")
     ap.add_argument("--emulate", default="", help="diagnostic, one GPU: R/W = the shard rank R of a W-rank job would hold")
     return ap.parse_args()
 
@@ -176,12 +182,83 @@ def gen_codes(n_sets, G, p):
     return synth.phylogeny_sequences(n_sets, G, p), "numpy generator (same distribution, other sets than the GPU arm)"
 
 
-def write_spss(codes, path, piece=100000):
+def write_spss(codes, path, piece=100000, k=K):
     """one sequence as an SPSS-like text file: overlapping pieces spelling the same k-mers"""
     import synth
     with open(path, "wb") as fh:
-        for s in synth.split_strings(codes, K, piece):
+        for s in synth.split_strings(codes, k, piece):
             fh.write(s + b"\n")
+
+
+C1_MERGES = 3
+
+
+def c1_files(tmp):
+    """BASELINE configs[0] (C1): 8 sets of ~1 M canonical 15-mers, 1 Mbp windows of one 2 Mbp genome, p = 0.005"""
+    import synth
+    files = []
+    for i, s in enumerate(synth.window_sequences(8, 2_000_000, 1_000_000, 0.005)):
+        f = os.path.join(tmp, f"c1_{i}.txt")
+        write_spss(s, f, k=15)
+        files.append(f)
+    return files
+
+
+def reference_extras(seqs, cores):
+    """the two other baselines BASELINE.md section 3 promises, with the reference's own code:
+    (2) the split of one greedy iteration on two full-size sets (kmer_set_set.h:332-343),
+    (4) kmerset-multiple-compress end to end on C1, bounded to its first C1_MERGES merges"""
+    from _oracle import Ref, set_ref_seed
+    if not Ref.available():
+        return None, None
+    ref = Ref()
+    ref.lib.ref_set_log_level(4)
+    tmp = tempfile.mkdtemp(prefix="kmsc_refx_")
+    fj, fk = os.path.join(tmp, "j.txt"), os.path.join(tmp, "k.txt")
+    write_spss(seqs[0], fj)
+    write_spss(seqs[1], fk)
+    sec, sizes = ref.split_stage(4, fj, fk, True, cores)
+    keys = int(sizes[0] + sizes[1] + sizes[2] + sizes[3] + sizes[4])
+    split = {"value": keys / sum(sec), "unit": "input+output keys/s", "seconds": sum(sec), "decode_s": sec[0], "intersection_s": sec[1],
+             "sub_s": sec[2], "sizes": [int(x) for x in sizes],
+             "what": f"ToKmerSet x2 + Intersection + Sub x2 on sets 0 and 1 (kmer_set_set.h:332-343), n_workers={cores}"}
+    os.remove(fj)
+    os.remove(fk)
+    files = c1_files(tmp)
+    set_ref_seed(77)
+    t0 = time.time()
+    out = ref.kmer_set_set(2, files, True, n_workers=cores, stop_after_weights=-C1_MERGES)
+    dt = time.time() - t0
+    c1 = {"seconds": dt, "merges": C1_MERGES, "unit": "s",
+          "what": f"C1: reference KmerSetSet constructor on 8 sets x 1M 15-mers up to its merge {C1_MERGES + 1} (n_workers={cores}); "
+                  "the GPU arm's `c1` runs the same bounded job through its executable"} if out["rc"] in (0, 1) else None
+    for f in files:
+        os.remove(f)
+    os.rmdir(tmp)
+    return split, c1
+
+
+def ours_c1():
+    """C1 through this repository's kmerset-multiple-compress, bounded like reference_extras"""
+    host = ROOT / "kmer-sets-compression_b200" / "host"
+    if subprocess.run(["make", "-s", "-C", str(host)], capture_output=True).returncode != 0:
+        return None
+    tmp = tempfile.mkdtemp(prefix="kmsc_c1_")
+    files = c1_files(tmp)
+    t0 = time.time()
+    r = subprocess.run([str(host / "bin" / "kmerset-multiple-compress"), "--k=15", "--seed=77", f"--max_iterations={C1_MERGES}"] + files,
+                       capture_output=True, text=True, timeout=900)
+    wall = time.time() - t0
+    for f in files:
+        os.remove(f)
+    os.rmdir(tmp)
+    if r.returncode != 0:
+        return {"error": r.stderr[-300:]}
+    import re
+    m = re.search(r"merges = (\d+), seconds = ([0-9.]+)", r.stderr)
+    return {"seconds": float(m.group(2)) if m else None, "merges": int(m.group(1)) if m else None, "process_wall_s": wall, "unit": "s",
+            "what": f"C1: this repository's KmerSetSet constructor (device sets + host SPSS re-encode of the changed nodes) on 8 sets x 1M "
+                    f"15-mers, first {C1_MERGES} merges; process_wall_s adds file loading and CUDA start-up"}
 
 
 def reference_exact(seqs, steps, warmup, cores, n_total):
@@ -263,11 +340,220 @@ def reference_sampled(seqs, cores):
                     f"all {len(seqs)} sets, n_workers={cores}"}
 
 
+def peaks_file():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        return {}
+
+
+def run_c5(args, out):
+    """BASELINE configs[4]: k = 15 dense-bitmap path, 512 sets, AND-popcount Gram (one GPU).
+    Every set becomes a 2^30-bit bitmap (128 MiB); W = B B^T as tcgen05 kind::i8 MMAs on the 0/1-expanded
+    bitmap words (csrc/bitmap.cu). The contraction is tensor-pipe bound, not HBM bound:
+    both fractions are reported. Timing input: random k-mer sets (AND+POPC time does not depend on the
+    density); parity: entries of W against the oracle's merge count."""
+    import torch
+    import kmsc
+    from _oracle import Oracle
+    K5, N5, KB5 = 15, 14, 2
+    n = args.sets if args.sets > 0 else 512
+    per_set = min(args.kmers, 2_000_000)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = kmsc.Context(0, stream.cuda_stream)
+    g = torch.Generator(device=dev)
+    g.manual_seed(777)
+    base = torch.unique(torch.randint(0, 1 << 30, (per_set,), dtype=torch.int64, device=dev, generator=g))
+    sets, host_sets = [], {}
+    for i in range(n):
+        # related sets: a random 90 % of a common pool plus a few private k-mers
+        keep = torch.rand(base.numel(), device=dev, generator=g) < 0.9
+        extra = torch.randint(0, 1 << 30, (per_set // 20,), dtype=torch.int64, device=dev, generator=g)
+        km = torch.unique(torch.cat([base[keep], extra])).cpu().numpy().astype(np.uint64)
+        sets.append(ctx.set_from_kmers(K5, N5, KB5, km))
+        if i in (0, 1, n - 1):
+            host_sets[i] = km
+    sampler = ClockSampler(0)
+    for _ in range(max(1, args.warmup)):
+        W = ctx.bitmap_gram(sets)
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        W = ctx.bitmap_gram(sets)          # bitmap fill + Gram + D2H of the matrix: the public call
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    o = Oracle()
+    for i, j in ((0, 1), (0, n - 1), (1, n - 1)):
+        want = int(o.merge_count(host_sets[i], host_sets[j]))
+        assert int(W[i, j]) == want == int(W[j, i]), f"W[{i},{j}] = {int(W[i, j])}, oracle {want}"
+    for i in host_sets:
+        assert int(W[i, i]) == len(host_sets[i])
+    bitmap_bytes = n * (1 << 27)
+    blocks = -(-n // 256)
+    macs = (blocks * (blocks + 1) // 2) * 256 * 256 * (1 << 30) if n > 128 else n * n * (1 << 30)
+    word_ops = n * (n + 1) // 2 * (1 << 25)
+    pk = peaks_file()
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    # int8 dense tensor peak: no measured entry; nominal 4.5 POP/s scaled by this pool's measured/nominal bf16 ratio
+    int8_peak = 4500.0 * float(pk.get("bf16_tflops", 1590.0)) / 2250.0
+    line = {"metric": "k=15 dense-bitmap Gram: AND-popcount 32-bit word-pairs per second (sets x sets x 2^25 words)",
+            "value": word_ops / (ms / 1e3), "unit": "word-pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (0/1) x u8 -> s32 on tcgen05",
+            "data": "synthetic", "config": {"workload": f"C5: {n} sets, k=15 bitmaps of 2^30 bits ({bitmap_bytes / 2**30:.0f} GiB), all-pairs AND-popcount Gram",
+                                            "n_sets": n, "k": 15, "kmers_per_set": int(sets[0].n_keys),
+                                            "l2": "64 GiB of bitmaps stream through the 126 MB L2; no flush needed"},
+            "e2e": {"value": word_ops / (ms / 1e3), "unit": "word-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * n * 8,
+                    "note": "the sets are device-resident handles (the reference's KmerSet objects); the call builds the bitmaps, "
+                            "runs the Gram and returns the matrix to the host"},
+            "gpu_launches": int(ctx.launch_count() - launches0), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "bitmap_gram_tc_kernel", "achieved": 2 * macs / (ms / 1e3) / 1e12, "peak": int8_peak,
+                         "unit": "TOP/s (int8)", "frac": 2 * macs / (ms / 1e3) / 1e12 / int8_peak, "traffic": None,
+                         "peak_source": "nominal 4.5 POP/s dense int8 x (measured bf16 / nominal bf16) of MEASURED_PEAKS.json: no int8 entry is measured",
+                         "hbm": {"achieved_gbs": bitmap_bytes / (ms / 1e3) / 1e9, "peak": hbm, "frac": bitmap_bytes / (ms / 1e3) / 1e9 / hbm,
+                                 "algorithmic_bytes": bitmap_bytes},
+                         "note": "time includes the bitmap fill and the D2H of the matrix (the whole public call)"},
+            "oracle_check": {"entries": 6, "ok": True}}
+    print(json.dumps(line), file=out, flush=True)
+
+
+def gen_fasta_torch(n_bytes, read_len, genome_len, dev):
+    """synthetic 2-line FASTA records on the GPU: reads of a random genome, both strands, 0.1 %
+    substitutions, one N per 10 000 reads; fixed-width headers so that the file is a byte matrix"""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(2024)
+    hdr = 10                                   # ">r" + 8 digits
+    rec = hdr + 1 + read_len + 1
+    n_reads = max(1, n_bytes // rec)
+    genome = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=dev, generator=g)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    out = torch.empty((n_reads, rec), dtype=torch.uint8, device=dev)
+    step = 1 << 20
+    ar = torch.arange(read_len, device=dev)
+    for a in range(0, n_reads, step):
+        b = min(n_reads, a + step)
+        m = b - a
+        start = torch.randint(0, genome_len - read_len, (m,), device=dev, generator=g)
+        codes = genome[start[:, None] + ar[None, :]]
+        rcm = torch.rand(m, device=dev, generator=g) < 0.5
+        codes = torch.where(rcm[:, None], (3 - codes).flip(1), codes)
+        err = torch.rand((m, read_len), device=dev, generator=g) < 0.001
+        codes = torch.where(err, (codes + torch.randint(1, 4, (m, read_len), dtype=torch.uint8, device=dev, generator=g)) & 3, codes)
+        seq = lut[codes.long()]
+        hasn = torch.rand(m, device=dev, generator=g) < 1e-4
+        pos = torch.randint(0, read_len, (m,), device=dev, generator=g)
+        seq[hasn.nonzero().flatten(), pos[hasn]] = 78   # 'N'
+        ids = torch.arange(a, b, device=dev)
+        out[a:b, 0] = 62
+        out[a:b, 1] = 114
+        for d in range(8):
+            out[a:b, 2 + d] = (48 + (ids // (10 ** (7 - d))) % 10).to(torch.uint8)
+        out[a:b, hdr] = 10
+        out[a:b, hdr + 1:hdr + 1 + read_len] = seq
+        out[a:b, rec - 1] = 10
+    return out, rec
+
+
+def run_c4(args, out):
+    """BASELINE configs[3]: kmerset-build counting on synthetic FASTA reads, k = 31, cutoff 4
+    (KmerCounter::FromFASTA + ToKmerSet, reference lib/core/kmer_counter.h:64-243). A slice of the 20 GB
+    file (--bytes) streams from pinned host memory through the chunked counter (kmsc_counter_*);
+    metric = bases counted per second end to end. The reference's own KmerCounter runs beside it on a
+    bounded slice with all host threads."""
+    import torch
+    import kmsc
+    K4, N4, KB4 = 31, 14, 8
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = kmsc.Context(0, stream.cuda_stream)
+    read_len = 150
+    genome_len = 20_000_000
+    recs, rec = gen_fasta_torch(args.bytes, read_len, genome_len, dev)
+    n_reads = recs.shape[0]
+    host = torch.empty(recs.numel(), dtype=torch.uint8, pin_memory=True)
+    host.copy_(recs.flatten())
+    del recs
+    torch.cuda.synchronize()
+    data = host.numpy()
+    per_chunk = max(1, args.chunk_bytes // rec) * rec
+    chunks = [data[a:a + per_chunk] for a in range(0, len(data), per_chunk)]
+    bases = n_reads * read_len
+
+    def step():
+        s, cut, nd = ctx.count_chunks(K4, N4, KB4, chunks, canonical=True, cutoff=4, fasta=True)
+        r = (s.n_keys, cut, nd)
+        s.free()
+        return r
+
+    sampler = ClockSampler(0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        res = step()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = ctx.launch_count()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.time()
+    for _ in range(steps):
+        res = step()
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / steps
+    clocks = sampler.stop()
+    # parity on a slice against the oracle (FromReads semantics) and the reference's own counter beside it
+    from _oracle import Oracle, Ref
+    o = Oracle()
+    n_chk = min(n_reads, 20000)
+    reads_chk = [bytes(data[i * rec + 11:i * rec + 11 + read_len]).decode() for i in range(n_chk)]
+    km, cnt = o.count_reads(reads_chk, K4, True)
+    kept, cut_o = o.counter_to_set(km, cnt, 2)
+    s2, cut2, nd2 = ctx.count_fasta(K4, N4, KB4, bytes(data[:n_chk * rec]), canonical=True, cutoff=2)
+    assert (s2.n_keys, cut2, nd2) == (len(kept), cut_o, len(km)), "counting differs from the oracle on the check slice"
+    assert s2.Hash() == o.set_hash(kept)
+    cpu = None
+    if Ref.available() and not args.no_cpu_baseline:
+        ref = Ref()
+        n_ref = min(n_reads, 400_000)
+        reads_ref = [bytes(data[i * rec + 11:i * rec + 11 + read_len]).decode() for i in range(n_ref)]
+        t1 = time.time()
+        ref.count_reads(5, reads_ref, True, 4, n_workers=os.cpu_count() or 1)
+        t_ref = time.time() - t1
+        cpu = {"value": n_ref * read_len / t_ref, "unit": "bases/s", "cores": os.cpu_count() or 1, "kind": "reference",
+               "sample": f"KmerCounter::FromReads + ToKmerSet(4) (+ the test driver's read-back of the counts) on the first {n_ref} reads "
+                         f"({n_ref * read_len / 1e6:.0f} Mbases), n_workers = all cores; {t_ref:.1f} s"}
+    pk = peaks_file()
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    line = {"metric": "k-mer counting throughput, FASTA bytes in host memory -> counted set (k=31, cutoff 4)", "value": bases / dt,
+            "unit": "bases/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"C4 slice: {len(data) / 1e9:.2f} GB of 2-line FASTA ({n_reads} reads x {read_len} bp, both strands, 0.1% "
+                                   f"substitutions, genome {genome_len} bp), canonical 31-mers <31,14,uint64>, cutoff 4, streamed in "
+                                   f"{len(chunks)} chunks of whole records", "k": 31, "cutoff": 4, "bytes": int(len(data)),
+                       "l2": "every chunk (256 MB) exceeds the 126 MB L2"},
+            "e2e": {"value": bases / dt, "unit": "bases/s", "h2d_bytes_per_step": int(len(data)), "d2h_bytes_per_step": 64,
+                    "note": "value IS the end-to-end number: the bytes start in pinned host memory"},
+            "gpu_launches": int(ctx.launch_count() - launches0), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "P1 pipeline (classify/pack + partition sort + run-length count + merge)",
+                         "achieved": len(data) / dt / 1e9, "peak": hbm, "unit": "GB/s", "frac": len(data) / dt / 1e9 / hbm, "traffic": None,
+                         "note": "algorithmic bytes = the file read once; the step is bound by the per-chunk sort passes and the host-to-device copy"},
+            "result": {"kept": int(res[0]), "cutoff_count": int(res[1]), "distinct": int(res[2])},
+            "cpu_baseline": cpu, "oracle_check": {"reads": n_chk, "ok": True}}
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
     args = parse_args()
     strong = args.workload == "C3"
     if args.sets <= 0:
-        args.sets = 256 if strong else 64
+        args.sets = {"C3": 256, "C5": 512}.get(args.workload, 64)
     # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version
     # banner, for one) goes to stderr instead
     out = os.fdopen(os.dup(1), "w")
@@ -285,6 +571,11 @@ def main():
               "parallelism": f"prefix-sharded x{world}, all-reduce inside kmsc_pair_counts" if world > 1 else "single GPU",
               "l2": f"inputs ({args.sets * args.kmers * 4 / (1 if not strong else world) / 1e9:.2f} GB/GPU) exceed the 126 MB L2; no flush needed"}
 
+    if args.workload in ("C4", "C5") and args.impl != "reference":
+        if rank == 0:
+            (run_c4 if args.workload == "C4" else run_c5)(args, out)
+        return
+
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
@@ -297,6 +588,7 @@ def main():
         t_full = ex["waves"] * ex["t_decode_wave_s"] * world + visits_full / ex["pair_rate"]
         val = visits_full / t_full
         smp = None if args.no_ref_sampled else reference_sampled(seqs, cores)
+        split_ref, c1_ref = (None, None) if args.no_ref_sampled else reference_extras(seqs, cores)
         sample = (f"exact job of the config with the reference's code: GetSampledKmerSet over all {1 << N} buckets timed on one "
                   f"wave of {ex['wave_sets']} of the {args.sets} sets ({ex['t_decode_wave_s']:.2f} s, one task per set), then each step = "
                   f"the all-pairs two-pointer merge over those {ex['wave_sets']} sets on {cores} threads ({ex['pair_step_s']:.3f} s, "
@@ -311,7 +603,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ex["kind"], "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "phases": {k: ex[k] for k in ("t_decode_wave_s", "wave_sets", "waves", "pair_rate", "pair_step_s", "visits_step")},
-                "sampled": smp, "gpu_launches": 0}
+                "sampled": smp, "split_stage": split_ref, "c1": c1_ref, "gpu_launches": 0}
         print(json.dumps(line), file=out, flush=True)
         return
 
@@ -454,6 +746,7 @@ def main():
     # (north_star: MST over d(i,j) = |Si| + |Sj| - 2 W[i][j]; per edge the two difference sets
     # via kmsc_pair_split). Bytes are the algorithmic B_w + sum B_s of SURVEY 8(d).
     stage = None
+    split_pair = None
     if not args.no_stage:
         sizes = np.diag(W).astype(np.int64)
         dist_m = sizes[:, None] + sizes[None, :] - 2 * W
@@ -495,6 +788,23 @@ def main():
         split_ms = es0.elapsed_time(es1) / split_reps
         w_ms = ms / args.steps
         w_bytes = algo_bytes / max(1, main_launches)
+        # one greedy-iteration split (n, j \\ n, k \\ n) of sets 0 and 1: the reference arm's `split_stage`
+        if world == 1:
+            for _ in range(2):
+                for x in ctx.pair_split(sets[0], sets[1]):
+                    x.free()
+            barrier()
+            es0.record(stream)
+            for _ in range(5):
+                outs3 = ctx.pair_split(sets[0], sets[1])
+                k3 = sets[0].n_keys + sets[1].n_keys + sum(x.n_keys for x in outs3)
+                for x in outs3:
+                    x.free()
+            es1.record(stream)
+            barrier()
+            pair_ms = es0.elapsed_time(es1) / 5
+            split_pair = {"value": k3 / (pair_ms / 1e3), "unit": "input+output keys/s", "ms": pair_ms,
+                          "what": "kmsc_pair_split of sets 0 and 1, all three outputs, sets resident on the device"}
         stage = {"what": "all-pairs matrix + the two difference sets of each of the n-1 MST edges (one kmsc_pair_split_batch), per GPU",
                  "ms": w_ms + split_ms, "weights_ms": w_ms, "splits_ms": split_ms, "n_splits": len(edges),
                  "algorithmic_bytes": w_bytes + split_bytes,
@@ -522,12 +832,25 @@ def main():
         m_own = n // world if world > 1 and n % world == 0 else 0
         cuts_np = np.asarray(cuts, np.int32) if world > 1 else None
 
+        phase_ms = {}
+
+        def timed(name, fn):
+            if not args.profile_e2e:
+                return fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            phase_ms[name] = phase_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+            return r
+
         def step_e2e_exchange():
             mine = [rank + j * world for j in range(m_own)]
-            full = ctx.sets_from_packed_batch(K, N, KB, None, [str_offs] * m_own, words_ptrs=[pinned[i].data_ptr() for i in mine])
-            ss = ctx.sets_exchange(full, cuts_np, n)     # one grouped NCCL exchange inside the library
-            ctx.pair_counts_device(ss, d_out.data_ptr())
-            host_out[:] = d_out.cpu().numpy().reshape(n, n)
+            full = timed("decode", lambda: ctx.sets_from_packed_batch(K, N, KB, None, [str_offs] * m_own,
+                                                                    words_ptrs=[pinned[i].data_ptr() for i in mine]))
+            ss = timed("exchange", lambda: ctx.sets_exchange(full, cuts_np, n))     # one grouped NCCL exchange inside the library
+            timed("pair_counts", lambda: ctx.pair_counts_device(ss, d_out.data_ptr()))
+            host_out[:] = timed("d2h", lambda: d_out.cpu().numpy().reshape(n, n))
             for s in ss + full:
                 s.free()
 
@@ -547,6 +870,9 @@ def main():
             tt = torch.tensor([ms_e], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt[0])
+        if args.profile_e2e and phase_ms:
+            print(f"[rank {rank}] e2e phases, ms per step: " + ", ".join(f"{k} {v / (e2e_steps + 1):.2f}" for k, v in phase_ms.items()),
+                  file=sys.stderr, flush=True)
         assert np.array_equal(host_out, W), "e2e matrix differs from the resident run"
         # the reference's own mode: weights over a 2 % bucket sample (kmer_set_set.h:123-124), same sets
         if world == 1:
@@ -629,7 +955,8 @@ def main():
             "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage": stage, "cpu_baseline": cpu_baseline,
-            "sampled": sampled, "oracle_check": oracle_check,
+            "sampled": sampled, "split_stage": split_pair, "c1": (ours_c1() if world == 1 and not args.no_c1 else None),
+            "oracle_check": oracle_check,
             "check": {"W01": int(W[0, 1]), "W_diag0": int(W[0, 0]), "keys_per_gpu": int(keys_local),
                       "p3_stats": ctx.pair_counts_stats() if args.no_e2e and args.no_stage else None, "buckets": [int(lo), int(hi)]}}
     if per_rank is not None:

@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -43,7 +44,14 @@ NcclApi* nccl() {
   static bool tried = false;
   if (tried) return api.handle ? &api : nullptr;
   tried = true;
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  // 1. KMSC_NCCL_LIB names the library (a host program that will load its own NCCL later, e.g. a
+  //    Python process that imports torch after this point, must point here at that copy: two NCCL
+  //    builds under one SONAME cannot live in one process); 2. a copy already in the process;
+  //    3. the system's.
+  void* h = nullptr;
+  if (const char* e = getenv("KMSC_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!h) return nullptr;
 #define KMSC_SYM(field, name) *(void**)(&api.field) = dlsym(h, name); if (!api.field) return nullptr;

@@ -88,6 +88,7 @@ int partition_plan(kmsc_ctx* ctx, const PipelineInput* in, int m, const Pipeline
   // about twice over all jobs, and few enough that the scan's per-bin walk over them stays short
   const uint64_t max_tiles = (uint64_t)(max_pos + part::kTile - 1) / part::kTile;
   unsigned gx = (unsigned)std::max<int64_t>(1, (int64_t)ctx->sm_count * 4 / m);
+  if (const char* e = getenv("KMSC_P2_CTAS")) gx = (unsigned)std::max(1, atoi(e));
   if (gx > 256) gx = 256;
   if (gx > max_tiles) gx = (unsigned)max_tiles;
   plan->n_ctas = (int)gx;

@@ -84,6 +84,18 @@ class KmerSetCompact {
     return KmerSet<K, N, KeyType>(MakeSetPtr(Decode(canonical, true, bucket_lo, bucket_hi)));
   }
 
+  // the packed form the device decodes (2 bits per base, 32 bases per word, first base on top)
+  // and the string boundaries in bases: what kmsc_set_from_packed / kmsc_sets_from_packed_batch take
+  const std::vector<std::uint64_t>& PackedWords() const { return words_; }
+  std::vector<std::int64_t> StringOffsets() const {
+    const std::vector<std::uint32_t> lens = Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_));
+    std::vector<std::int64_t> offs(static_cast<std::size_t>(n_) + 1, 0);
+    for (std::int64_t i = 0; i < n_; i++)
+      offs[static_cast<std::size_t>(i) + 1] =
+          offs[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(lens[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(K));
+    return offs;
+  }
+
   std::vector<std::string> ToStrings(int /*n_workers*/) const {
     const std::vector<std::uint32_t> lens = Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_));
     std::vector<std::string> out(static_cast<std::size_t>(n_));
@@ -121,11 +133,7 @@ class KmerSetCompact {
   }
 
   kmsc_set* Decode(bool canonical, bool dedup, int bucket_lo, int bucket_hi) const {
-    const std::vector<std::uint32_t> lens = Svb0124Decode(lengths_compressed_, static_cast<std::size_t>(n_));
-    std::vector<std::int64_t> offs(static_cast<std::size_t>(n_) + 1, 0);
-    for (std::int64_t i = 0; i < n_; i++)
-      offs[static_cast<std::size_t>(i) + 1] =
-          offs[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(lens[static_cast<std::size_t>(i)] + static_cast<std::uint32_t>(K));
+    const std::vector<std::int64_t> offs = StringOffsets();
     kmsc_set* s = nullptr;
     std::lock_guard<std::mutex> l(Device::Mu());
     Device::Check(kmsc_set_from_packed(Device::Ctx(), K, N, static_cast<int>(sizeof(KeyType)), words_.data(), offs.data(), n_,

@@ -348,6 +348,8 @@ class KmerSetSetReader {
 };
 
 // ---- mst driver ---------------------------------------------------------------------------
+struct MstEdge;
+inline std::vector<MstEdge> MstTree(const std::vector<std::int64_t>& W, int n);
 struct MstEdge {
   int parent, child;
   std::int64_t distance;  // |S_p ^ S_c| (symmetric difference)
@@ -364,17 +366,16 @@ struct MstResult {
 // Minimum spanning tree of the symmetric-difference graph: edges sorted by
 // (d ascending, i ascending, j ascending), Kruskal with ParallelDisjointSet, tree
 // oriented by BFS from set 0, the difference sets of all edges from one batched device split.
-template <int K, int N, typename KeyType>
-MstResult<K, N, KeyType> BuildMst(const std::vector<KmerSet<K, N, KeyType>>& sets) {
-  using Set = KmerSet<K, N, KeyType>;
-  MstResult<K, N, KeyType> r;
-  const int n = static_cast<int>(sets.size());
-  r.W = KmerSetSet<K, N, KeyType>::PairCounts(sets, nullptr);
+// The tree itself, from an exact n x n intersection matrix (diagonal = set sizes): candidate edges by
+// (d ascending, i ascending, j ascending), Kruskal with ParallelDisjointSet, oriented breadth-first from
+// set 0 with neighbours in ascending order. Shared by the single-GPU and the multi-GPU driver.
+inline std::vector<MstEdge> MstTree(const std::vector<std::int64_t>& W, int n) {
+  std::vector<MstEdge> edges;
   std::vector<std::tuple<std::int64_t, int, int>> cand;
   for (int i = 0; i < n; i++)
     for (int j = i + 1; j < n; j++) {
-      const std::int64_t d = r.W[static_cast<std::size_t>(i) * n + i] + r.W[static_cast<std::size_t>(j) * n + j] -
-                             2 * r.W[static_cast<std::size_t>(i) * n + j];
+      const std::int64_t d = W[static_cast<std::size_t>(i) * n + i] + W[static_cast<std::size_t>(j) * n + j] -
+                             2 * W[static_cast<std::size_t>(i) * n + j];
       cand.emplace_back(d, i, j);
     }
   std::sort(cand.begin(), cand.end());
@@ -397,10 +398,20 @@ MstResult<K, N, KeyType> BuildMst(const std::vector<KmerSet<K, N, KeyType>>& set
     for (const auto& e : adj[static_cast<std::size_t>(p)]) {
       if (seen[static_cast<std::size_t>(e.first)]) continue;
       seen[static_cast<std::size_t>(e.first)] = true;
-      r.edges.push_back({p, e.first, e.second});
+      edges.push_back({p, e.first, e.second});
       q.push(e.first);
     }
   }
+  return edges;
+}
+
+template <int K, int N, typename KeyType>
+MstResult<K, N, KeyType> BuildMst(const std::vector<KmerSet<K, N, KeyType>>& sets) {
+  using Set = KmerSet<K, N, KeyType>;
+  MstResult<K, N, KeyType> r;
+  const int n = static_cast<int>(sets.size());
+  r.W = KmerSetSet<K, N, KeyType>::PairCounts(sets, nullptr);
+  r.edges = MstTree(r.W, n);
   // the difference sets of all n - 1 tree edges in one streaming device pass; the exact matrix
   // gives every |S_p & S_c|, so the outputs are allocated exactly and written directly
   std::vector<const Set*> js, ks;

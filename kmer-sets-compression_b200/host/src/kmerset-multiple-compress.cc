@@ -7,7 +7,10 @@
 // --max_iterations, --driver=greedy|mst (mst: Kruskal over the exact symmetric-difference
 // matrix + one difference-set pair per tree edge; its own directory layout, see DumpMst),
 // --trace=<file> (weight matrix, merges / tree edges with the sizes and XOR hashes of the
-// difference sets: what the parity tests compare with the oracle).
+// difference sets: what the parity tests compare with the oracle), --gpus=N (mst driver: the
+// k-mer prefix space is sharded over N GPUs of this box, one host thread and one NCCL rank per
+// GPU; the number of sets must be a multiple of N).
+#include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <string>
@@ -16,6 +19,7 @@
 #include "flags.h"
 #include "kmsc/kmer_set_compact.h"
 #include "kmsc/kmer_set_set.h"
+#include "kmsc/multi_gpu.h"
 
 using namespace kmsc;
 using namespace kmsc_cli;
@@ -39,9 +43,22 @@ int Main(const Flags& flags) {
   const std::string out = flags.Str("out", "");
   if (flags.Str("driver", "greedy") == "mst") {
     Info("constructing the spanning tree");
-    std::vector<KmerSet<K, N, KeyType>> ksets;
-    for (const auto& c : sets) ksets.push_back(c.ToKmerSet(canonical, n_workers));
-    const MstResult<K, N, KeyType> r = BuildMst<K, N, KeyType>(ksets);
+    const int n_gpus = flags.Int("gpus", 1);
+    MstResult<K, N, KeyType> r;
+    if (n_gpus > 1) {
+      MultiGpuMst<K, N, KeyType> mg = BuildMstMultiGpu<K, N, KeyType>(sets, canonical, n_gpus);
+      if (!mg.error.empty()) { Error("multi-GPU spanning tree failed: " + mg.error); return 1; }
+      r.W = std::move(mg.W);
+      r.edges = mg.edges;
+      for (std::size_t i = 0; i < r.edges.size(); i++) {
+        r.add.push_back(KmerSet<K, N, KeyType>::FromSortedBits(std::move(mg.add[i])));
+        r.del.push_back(KmerSet<K, N, KeyType>::FromSortedBits(std::move(mg.del[i])));
+      }
+    } else {
+      std::vector<KmerSet<K, N, KeyType>> ksets;
+      for (const auto& c : sets) ksets.push_back(c.ToKmerSet(canonical, n_workers));
+      r = BuildMst<K, N, KeyType>(ksets);
+    }
     Info("constructed the spanning tree, edges = " + std::to_string(r.edges.size()));
     if (!trace.empty()) {
       std::ofstream t(trace);
@@ -73,8 +90,10 @@ int Main(const Flags& flags) {
     if (opt.bucket_ids.empty()) { Error("no bucket ids in " + ids_file); return 1; }
   }
   const std::size_t n0 = sets.size();
+  const auto t_ctor = std::chrono::steady_clock::now();
   KmerSetSet<K, N, KeyType> kss(std::move(sets), canonical, n_workers, opt);
-  Info("constructed kmer_set_set, size = " + std::to_string(kss.Size()));
+  Info("constructed kmer_set_set, size = " + std::to_string(kss.Size()) + ", merges = " + std::to_string(kss.Merges().size()) +
+       ", seconds = " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ctor).count()));
   if (!trace.empty()) {
     std::ofstream t(trace);
     t << "driver greedy\nn " << n0 << "\nW";

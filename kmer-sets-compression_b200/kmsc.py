@@ -60,6 +60,19 @@ def lib() -> C.CDLL:
         return _lib
     if not LIB_PATH.exists():
         raise KmscError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    # one NCCL per process: if this interpreter has (or will import) torch, the communicator must use
+    # torch's bundled libnccl.so.2, not the system's (same SONAME, other version)
+    if "KMSC_NCCL_LIB" not in os.environ:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for base in (spec.submodule_search_locations if spec else []):
+                cand = Path(base) / "lib" / "libnccl.so.2"
+                if cand.exists():
+                    os.environ["KMSC_NCCL_LIB"] = str(cand)
+                    break
+        except Exception:
+            pass
     L = C.CDLL(str(LIB_PATH))
     L.kmsc_last_error.restype = C.c_char_p
     L.kmsc_version.restype = C.c_char_p
@@ -115,8 +128,8 @@ def lib() -> C.CDLL:
     L.kmsc_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.kmsc_sets_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, _i32p, C.POINTER(C.c_void_p), C.c_int32]
     L.kmsc_counter_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    L.kmsc_counter_add_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
-    L.kmsc_counter_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
+    L.kmsc_counter_add_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.kmsc_counter_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.kmsc_counter_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _i64p, _i64p]
     L.kmsc_counter_free.argtypes = [C.c_void_p, C.c_void_p]
     L.kmsc_counter_free.restype = None
@@ -414,8 +427,9 @@ class Context:
         _check(lib().kmsc_counter_create(self.h, K, N, key_bytes, int(canonical), C.byref(c)))
         try:
             add = lib().kmsc_counter_add_fasta if fasta else lib().kmsc_counter_add_reads
-            for ch in chunks:
-                _check(add(self.h, c, ch, len(ch)))
+            for ch in chunks:   # bytes, or a uint8 numpy view (e.g. of pinned memory)
+                ptr = ch.ctypes.data if isinstance(ch, np.ndarray) else C.cast(C.c_char_p(ch), C.c_void_p)
+                _check(add(self.h, c, ptr, len(ch)))
             h, cut, nd = C.c_void_p(), C.c_int64(), C.c_int64()
             _check(lib().kmsc_counter_finish(self.h, c, cutoff, C.byref(h), C.byref(cut), C.byref(nd)))
         finally:

@@ -236,6 +236,8 @@ struct LogCapture {
   std::vector<double> stamps;  // seconds since start, one per line
   std::chrono::steady_clock::time_point t0;
   const char* stop_after = nullptr;
+  int stop_after_merges = 0;   // > 0: leave the greedy loop when its (m+1)-th iteration announces its pair
+  int merges_seen = 0;
 };
 LogCapture* g_capture = nullptr;
 struct StopRun {};
@@ -251,6 +253,8 @@ void Hook(const char* fmt, const char* formatted) {
         std::chrono::duration<double>(std::chrono::steady_clock::now() - c->t0).count());
   }
   if (c->stop_after && std::strcmp(fmt, c->stop_after) == 0) throw StopRun{};
+  // the per-iteration line of the greedy loop, kmer_set_set.h:324: "j = {}, k = {}, weight = {}"
+  if (c->stop_after_merges > 0 && std::strncmp(formatted, "j = ", 4) == 0 && ++c->merges_seen > c->stop_after_merges) throw StopRun{};
 }
 
 // Runs the reference's KmerSetSet constructor (kmer_set_set.h:109-427) on SPSS
@@ -272,7 +276,8 @@ int RunKmerSetSet(const char* const* files, std::int32_t n_files, int canonical,
   }
   LogCapture cap;
   cap.t0 = std::chrono::steady_clock::now();
-  if (stop_after_weights) cap.stop_after = "calculated initial weights";
+  if (stop_after_weights == 1) cap.stop_after = "calculated initial weights";
+  if (stop_after_weights < 0) cap.stop_after_merges = -stop_after_weights;  // -m: stop when merge m + 1 is announced
   g_capture = &cap;
   kmsc_shim::log_hook() = &Hook;
   int rc = 0;
@@ -317,6 +322,31 @@ int RunKmerSetSet(const char* const* files, std::int32_t n_files, int canonical,
     std::memcpy(*log_text, cap.text.c_str(), cap.text.size() + 1);
   }
   return rc;
+}
+
+// The split of one greedy iteration exactly as the reference does it (kmer_set_set.h:332-343):
+// ToKmerSet x2 (SPSS text -> hash sets), n = Intersection(j, k), j.Sub(n), k.Sub(n); seconds[0..2] =
+// decode, intersection, the two subtractions; sizes = |j|, |k|, |n|, |j \ n|, |k \ n|.
+template <int K, int N, typename KeyType>
+int SplitStage(const char* file_j, const char* file_k, int canonical, int n_workers, double* seconds, std::int64_t* sizes) {
+  auto lj = KmerSetCompact<K, N, KeyType>::Load(file_j, "");
+  auto lk = KmerSetCompact<K, N, KeyType>::Load(file_k, "");
+  if (!lj.ok() || !lk.ok()) return -1;
+  auto t0 = std::chrono::steady_clock::now();
+  KmerSet<K, N, KeyType> sj = lj.value().ToKmerSet(canonical != 0, n_workers);
+  KmerSet<K, N, KeyType> sk = lk.value().ToKmerSet(canonical != 0, n_workers);
+  auto t1 = std::chrono::steady_clock::now();
+  sizes[0] = sj.Size(); sizes[1] = sk.Size();
+  KmerSet<K, N, KeyType> n = Intersection(sj, sk, n_workers);
+  auto t2 = std::chrono::steady_clock::now();
+  sj.Sub(n, n_workers);
+  sk.Sub(n, n_workers);
+  auto t3 = std::chrono::steady_clock::now();
+  sizes[2] = n.Size(); sizes[3] = sj.Size(); sizes[4] = sk.Size();
+  seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+  seconds[1] = std::chrono::duration<double>(t2 - t1).count();
+  seconds[2] = std::chrono::duration<double>(t3 - t2).count();
+  return 0;
 }
 
 template <int K, int N, typename KeyType>
@@ -401,6 +431,12 @@ int ref_kmer_set_set(int cfg, const char* const* files, std::int32_t n_files, in
                      std::int64_t* sizes, std::uint64_t* hashes, std::int32_t* n_nodes,
                      const char* dump_dir) {
   KMSC_DISPATCH(cfg, C_KSS)
+}
+
+#define C_SPLIT(K, N, T) SplitStage<K, N, T>(file_j, file_k, canonical, n_workers, seconds, sizes)
+int ref_split_stage(int cfg, const char* file_j, const char* file_k, int canonical, int n_workers, double* seconds,
+                    std::int64_t* sizes) {
+  KMSC_DISPATCH(cfg, C_SPLIT)
 }
 
 #define C_READER(K, N, T) ReaderGet<K, N, T>(dir, canonical, n_workers, i, size, hash, n_sets)

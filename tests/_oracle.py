@@ -367,6 +367,7 @@ class Ref:
         L.ref_kmer_set_set.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int32, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_double), C.POINTER(C.c_void_p), i64p, u64p, i32p,
                                        C.c_char_p]
+        L.ref_split_stage.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_double), i64p]
         L.ref_reader_get.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int32, i64p, u64p, i32p]
         L.ref_random_ints.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, i32p]
         L.ref_seed_counter.restype = C.c_uint64
@@ -472,6 +473,15 @@ class Ref:
             self.lib.ref_free(log)
         return dict(rc=rc, phase_s=(phase[0], phase[1]), log=text, sizes=sizes[:n].copy(),
                     hashes=hashes[:n].copy(), n_nodes=nn.value)
+
+    def split_stage(self, cfg, file_j, file_k, canonical=True, n_workers=1):
+        """one greedy-iteration split as the reference does it (kmer_set_set.h:332-343): seconds of
+        (ToKmerSet x2, Intersection, Sub x2) and |j|, |k|, |n|, |j \\ n|, |k \\ n|"""
+        sec = (C.c_double * 3)()
+        sizes = np.zeros(5, np.int64)
+        rc = self.lib.ref_split_stage(cfg, str(file_j).encode(), str(file_k).encode(), int(canonical), n_workers, sec, _ptr(sizes, i64p))
+        assert rc == 0, rc
+        return list(sec), sizes
 
     def reader_get(self, cfg, directory, canonical, i, n_workers=1):
         size, h, ns = C.c_int64(), C.c_uint64(), C.c_int32()
