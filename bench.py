@@ -832,10 +832,13 @@ def main():
         m_own = n // world if world > 1 and n % world == 0 else 0
         cuts_np = np.asarray(cuts, np.int32) if world > 1 else None
 
-        phase_ms = {}
+        phase_ms, phase_calls = {}, {}
 
         def timed(name, fn):
             if not args.profile_e2e:
+                return fn()
+            phase_calls[name] = phase_calls.get(name, 0) + 1
+            if phase_calls[name] <= 2:   # connection set-up, allocation pools
                 return fn()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -859,6 +862,8 @@ def main():
         for s in sets:
             s.free()
         step_e2e()
+        if args.profile_e2e:
+            step_e2e()
         barrier()
         e0.record(stream)
         for _ in range(e2e_steps):
@@ -871,7 +876,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt[0])
         if args.profile_e2e and phase_ms:
-            print(f"[rank {rank}] e2e phases, ms per step: " + ", ".join(f"{k} {v / (e2e_steps + 1):.2f}" for k, v in phase_ms.items()),
+            print(f"[rank {rank}] e2e phases, ms per step: " + ", ".join(f"{k} {v / max(1, phase_calls[k] - 2):.2f}" for k, v in phase_ms.items()),
                   file=sys.stderr, flush=True)
         assert np.array_equal(host_out, W), "e2e matrix differs from the resident run"
         # the reference's own mode: weights over a 2 % bucket sample (kmer_set_set.h:123-124), same sets

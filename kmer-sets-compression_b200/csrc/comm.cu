@@ -16,11 +16,12 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "kmsc_common.cuh"
+#include "kmer_pipeline.cuh"
 
 namespace kmsc {
 namespace {
@@ -91,13 +92,14 @@ __global__ void cut_offsets_kernel(const CutJob* __restrict__ jobs, int n_sets, 
   table[t] = q <= R ? jobs[j].lev0[cuts[q]] : jobs[j].flag;
 }
 
-// received raw offset slices -> lev[0] of the imported sets: rebased, empty outside [lo, hi)
-struct ImportJob { const uint32_t* in; uint32_t* lev0; uint32_t n_keys; };
-__global__ void import_offsets_batch_kernel(const ImportJob* __restrict__ jobs, int lo, int hi, int n_buckets) {
+// received raw FINEST-level offset slices -> finest level of the imported sets: rebased, empty outside
+// [lo, hi) (in fine-bucket units); the coarser levels follow by striding (derive_levels_batch)
+struct ImportJob { const uint32_t* in; uint32_t* fine; uint32_t n_keys; };
+__global__ void import_offsets_batch_kernel(const ImportJob* __restrict__ jobs, uint32_t lo, uint32_t hi, uint32_t n_fine) {
   const ImportJob jb = jobs[blockIdx.y];
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > n_buckets) return;
-  jb.lev0[b] = b <= lo ? 0u : b >= hi ? jb.n_keys : jb.in[b - lo] - jb.in[0];
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x > n_fine) return;
+  jb.fine[x] = x <= lo ? 0u : x >= hi ? jb.n_keys : jb.in[x - lo] - jb.in[0];
 }
 
 }  // namespace
@@ -214,7 +216,11 @@ int kmsc_sets_exchange(kmsc_ctx* ctx, const kmsc_set* const* mine, int32_t n_min
 
   // 2. the sets this rank will hold: global set r + j * R (rank r's j-th set), restricted to [lo, hi)
   const int lo = cuts[me], hi = cuts[me + 1];
-  const int n_ent = hi - lo + 1;  // offset entries per set slice
+  const int F = s0->max_level;
+  for (int32_t j = 0; j < n_mine; j++) KMSC_TRY(set_ensure_levels(ctx, mine[j]));
+  // the offsets travel at the FINEST level (64 entries per bucket, +5 % on the keys): the receiver
+  // rebases them and derives the coarser levels by striding instead of binary-searching every level
+  const size_t n_ent = ((size_t)(hi - lo) << F) + 1;  // offset entries per set slice
   auto cleanup = [&]() { for (int32_t g = 0; g < n_total; g++) if (out[g]) { kmsc_set_free(ctx, out[g]); out[g] = nullptr; } };
   for (int r = 0; r < R; r++)
     for (int32_t j = 0; j < n_mine; j++) {
@@ -236,6 +242,9 @@ int kmsc_sets_exchange(kmsc_ctx* ctx, const kmsc_set* const* mine, int32_t n_min
   uint32_t* d_in = (uint32_t*)(d2 + o_in);
 
   // 3. one grouped exchange: keys zero-copy between the sets' arrays, offsets into the scratch
+  const bool dbg = getenv("KMSC_DEBUG_COMM") != nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (dbg) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], ctx->stream); }
   const uint32_t* my_tab = h_all + (size_t)me * n_mine * W;
   ncclResult_t gr = a->GroupStart();
   if (gr != ncclSuccess) { cleanup(); return nccl_fail(a, gr, "ncclGroupStart"); }
@@ -245,7 +254,8 @@ int kmsc_sets_exchange(kmsc_ctx* ctx, const kmsc_set* const* mine, int32_t n_min
       const size_t nk = (size_t)t[q + 1] - t[q];
       if (nk) gr = a->Send((const unsigned char*)mine[j]->keys + (size_t)t[q] * kb, nk * kb, ncclUint8, q, (ncclComm_t)ctx->comm, ctx->stream);
       if (gr == ncclSuccess)
-        gr = a->Send(mine[j]->lev[0] + cuts[q], (size_t)(cuts[q + 1] - cuts[q] + 1) * 4, ncclUint8, q, (ncclComm_t)ctx->comm, ctx->stream);
+        gr = a->Send(mine[j]->lev[F] + ((size_t)cuts[q] << F), (((size_t)(cuts[q + 1] - cuts[q]) << F) + 1) * 4, ncclUint8, q,
+                     (ncclComm_t)ctx->comm, ctx->stream);
     }
   for (int r = 0; r < R && gr == ncclSuccess; r++)
     for (int32_t j = 0; j < n_mine && gr == ncclSuccess; j++) {
@@ -259,20 +269,35 @@ int kmsc_sets_exchange(kmsc_ctx* ctx, const kmsc_set* const* mine, int32_t n_min
     if (gr == ncclSuccess) gr = ge;
   }
   if (gr != ncclSuccess) { cleanup(); return nccl_fail(a, gr, "grouped ncclSend / ncclRecv"); }
+  if (dbg) cudaEventRecord(ev[1], ctx->stream);
 
   // 4. offsets of every imported set in one launch, then the finer levels
   std::vector<ImportJob> imp((size_t)n_total);
-  for (int32_t g = 0; g < n_total; g++) imp[(size_t)g] = ImportJob{d_in + (size_t)g * n_ent, out[g]->lev[0], (uint32_t)out[g]->n_keys};
+  for (int32_t g = 0; g < n_total; g++) imp[(size_t)g] = ImportJob{d_in + (size_t)g * n_ent, out[g]->lev[F], (uint32_t)out[g]->n_keys};
   // (a pageable source is copied to the driver's staging before the call returns)
   cudaError_t e = cudaMemcpyAsync(d2 + o_imp, imp.data(), (size_t)n_total * sizeof(ImportJob), cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "exchange", __FILE__, __LINE__); }
-  import_offsets_batch_kernel<<<dim3((nb + 1 + 255) / 256, (unsigned)n_total), 256, 0, ctx->stream>>>((const ImportJob*)(d2 + o_imp), lo, hi, nb);
+  const uint32_t n_fine = (uint32_t)nb << F;
+  import_offsets_batch_kernel<<<dim3((n_fine + 1 + 255) / 256, (unsigned)n_total), 256, 0, ctx->stream>>>(
+      (const ImportJob*)(d2 + o_imp), (uint32_t)lo << F, (uint32_t)hi << F, n_fine);
   count_launch(ctx);
   e = cudaGetLastError();
   if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "exchange import", __FILE__, __LINE__); }
-  for (int32_t g = 0; g < n_total; g++) {
-    const int rc = set_build_levels(ctx, out[g]);
+  {
+    const int rc = derive_levels_batch(ctx, out, n_total);
     if (rc != KMSC_OK) { cleanup(); return rc; }
+  }
+  if (dbg) {
+    cudaEventRecord(ev[2], ctx->stream);
+    cudaEventSynchronize(ev[2]);
+    float t01 = 0, t12 = 0;
+    cudaEventElapsedTime(&t01, ev[0], ev[1]);
+    cudaEventElapsedTime(&t12, ev[1], ev[2]);
+    size_t sent = 0;
+    for (int q = 0; q < R; q++) for (int32_t j = 0; j < n_mine; j++) sent += ((size_t)my_tab[(size_t)j * W + q + 1] - my_tab[(size_t)j * W + q]) * kb;
+    fprintf(stderr, "[kmsc comm rank %d] send/recv %.3f ms (%.1f MB sent, %.1f GB/s), import + levels %.3f ms\n", me, t01, sent / 1e6,
+            sent / 1e6 / t01, t12);
+    for (auto& x : ev) cudaEventDestroy(x);
   }
   return KMSC_OK;
 }

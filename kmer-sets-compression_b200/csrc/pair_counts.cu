@@ -42,6 +42,7 @@ struct PlanParams {
   int n_sets;
   unsigned long long L;  // target keys per tile
   uint32_t span;      // forced tile boundary every `span` fine buckets
+  uint32_t row_lo, row_hi;  // fine buckets outside [row_lo, row_hi) hold no key of any set (a rank's prefix shard)
 };
 
 // ---------------------------------------------------------------------------
@@ -57,6 +58,11 @@ __global__ void plan_gather_kernel(const SetDesc* __restrict__ sets, PlanParams 
   const int stride = n + 1;
   const uint32_t x0 = blockIdx.x * 32u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (x0 + 32u < pp.row_lo || x0 > pp.row_hi) {
+    // outside the sets' bucket range: no keys, and no tile ever names these rows (plan_emit clamps)
+    if (threadIdx.x < 32 && x0 + threadIdx.x < pp.NF) totals[x0 + threadIdx.x] = 0u;
+    return;
+  }
   if (sel_bitmap && x0 < pp.NF) {
     // nothing selected in [x0, x0+32] (row x0+32 included: it may close a tile)? write zeros only
     bool any = false;
@@ -196,7 +202,7 @@ __global__ void plan_emit_kernel(const uint32_t* __restrict__ totals, PlanParams
         }
         if (p > pre) {  // skip empty tiles
           const uint32_t slot = atomicAdd(n_tiles, 1u);
-          if (slot < max_tiles) tiles[slot] = Tile{x, xe};
+          if (slot < max_tiles) tiles[slot] = Tile{max(x, pp.row_lo), min(xe, pp.row_hi)};  // the rows cut off are empty
         }
       }
     }
@@ -774,6 +780,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
 
 }  // namespace kmsc
 #include "pair_counts_stream.cuh"
+#include "pair_counts_whash.cuh"
 namespace kmsc {
 
 // ---------------------------------------------------------------------------
@@ -916,6 +923,46 @@ static int launch_stream_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_
   return launch_stream<KeyT, 128>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, fine_level, finest_level, max_tiles);
 }
 
+// the warp-private hash build (pair_counts_whash.cuh): n <= 64 related sets
+template <typename KeyT>
+static int launch_whash(kmsc_ctx* ctx, const SetDesc* d_sets, int n_sets, const uint32_t* d_offsT, const Tile* d_tiles,
+                        const uint32_t* d_ntiles, uint32_t* d_counter, unsigned long long* d_W, unsigned long long* d_stats,
+                        int fine_level, int finest_level, uint32_t max_tiles, int rho_q) {
+  constexpr int NS = 64;
+  using C = WhCfg<NS>;
+  const size_t smem = WhLayout<KeyT, NS>::total;
+  auto kern = pair_counts_whash_kernel<KeyT, NS>;
+  static int occ_cache[64] = {0};
+  int occ = ctx->device < 64 ? occ_cache[ctx->device] : 0;
+  if (occ == 0) {
+    KMSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    KMSC_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int smem_sm = 0, smem_res = 0, regs_sm = 0, thr_sm = 0;
+    KMSC_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->device));
+    KMSC_CUDA(cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, ctx->device));
+    occ = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + (size_t)smem_res));
+    const int regs_per_cta = ((fa.numRegs + 7) & ~7) * C::T;
+    if (regs_per_cta > 0) occ = std::min(occ, regs_sm / regs_per_cta);
+    occ = std::min(occ, thr_sm / C::T);
+    occ = std::min(occ, 512 / NS);  // tensor-memory columns
+    if (occ < 1) { set_error("pair_counts whash kernel does not fit on an SM (smem %zu, %d regs)", smem, fa.numRegs); return KMSC_E_CUDA; }
+    if (getenv("KMSC_DEBUG"))
+      fprintf(stderr, "[kmsc] pair_counts whash NS=%d T=%d smem=%zu regs=%d -> %d CTAs per SM\n", NS, C::T, smem, fa.numRegs, occ);
+    if (ctx->device < 64) occ_cache[ctx->device] = occ;
+  }
+  long long grid = (long long)ctx->sm_count * occ;
+  if (grid > (long long)max_tiles) grid = max_tiles;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, C::T, smem, ctx->stream>>>(d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, fine_level,
+                                                    finest_level, rho_q);
+  count_launch(ctx);
+  KMSC_CUDA(cudaGetLastError());
+  return KMSC_OK;
+}
+
 template <typename KeyT>
 static int launch_main_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_sets,
                           const uint32_t* d_offsT, const Tile* d_tiles, const uint32_t* d_ntiles,
@@ -927,6 +974,8 @@ static int launch_main_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_se
     default: return launch_main<KeyT, 256>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
   }
 }
+
+constexpr int kWhashOverflow = 1000;  // internal: run_phase's "redo with another build"
 
 static int dmax_for(int ns, int tk_bytes) {
   if (ns == 64) return PcCfg<64, 4>::D;
@@ -944,9 +993,10 @@ struct PcDev {
 
 // One pass: plan tiles over the buckets selected by h_bitmap (NULL = all) with
 // tile target L, then run the main kernel accumulating into d_W.
-static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, bool merge_build,
+static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, int build,
                      const uint32_t* h_bitmap, unsigned long long L, double keys_in_phase,
-                     unsigned long long* d_W, unsigned long long host_stats[4]) {
+                     unsigned long long* d_W, unsigned long long host_stats[4], int rho_q = 1) {
+  const bool merge_build = build == 1;   // 0 hash table per CTA, 1 warp-wide merge, 2 warp-private hash tables
   const kmsc_set* s0 = sets[0];
   for (int i = 0; i < n; i++) KMSC_TRY(set_ensure_levels(ctx, sets[i]));
   const int nb = 1 << s0->N;
@@ -997,12 +1047,22 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, 
   PlanParams pp;
   pp.NF = NF; pp.f = f; pp.n_sets = n; pp.L = L;
   {
+    int span_lo = nb, span_hi = 0;
+    for (int i = 0; i < n; i++) {
+      span_lo = std::min(span_lo, sets[i]->b_lo < 0 ? 0 : sets[i]->b_lo);
+      span_hi = std::max(span_hi, sets[i]->b_hi < 0 ? nb : sets[i]->b_hi);
+    }
+    if (span_lo >= span_hi) { span_lo = 0; span_hi = nb; }
+    pp.row_lo = (uint32_t)span_lo << f;
+    pp.row_hi = (uint32_t)span_hi << f;
+  }
+  {
     // a tile may span several buckets only while (bucket - first bucket, key) fits
     // the table key: uint32 for 2/4-byte keys, uint64 for 8-byte keys
     const int tk_bits = s0->key_bytes == 8 ? 64 : 32;
     const int spare = tk_bits - s0->key_bits;
     // (the merge build has no table key: its tiles may always span buckets)
-    const uint32_t bucket_span = (spare >= 8 || merge_build) ? 256u : (1u << spare);
+    const uint32_t bucket_span = (spare >= 8 || build != 0) ? 256u : (1u << spare);
     const uint64_t span = (uint64_t)bucket_span << f;
     pp.span = span > 256 ? 256u : (uint32_t)span;
   }
@@ -1019,7 +1079,13 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, 
   }
   KMSC_CUDA(cudaEventRecord(ctx->pc_ev[1], ctx->stream));
   int rc;
-  if (merge_build) {
+  if (build == 2) {
+    switch (s0->key_bytes) {
+      case 2: rc = launch_whash<uint16_t>(ctx, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles, rho_q); break;
+      case 4: rc = launch_whash<uint32_t>(ctx, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles, rho_q); break;
+      default: rc = launch_whash<unsigned long long>(ctx, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles, rho_q); break;
+    }
+  } else if (merge_build) {
     switch (s0->key_bytes) {
       case 2: rc = launch_stream_ns<uint16_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles); break;
       case 4: rc = launch_stream_ns<uint32_t>(ctx, ns, d.sets, n, d_offsT, d_tiles, d.n_tiles, d.counter, d_W, d.stats, f, s0->max_level, max_tiles); break;
@@ -1050,6 +1116,7 @@ static int run_phase(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int ns, 
     ctx->pc_algo_bytes += (double)h_stats[0] * s0->key_bytes + (double)(nb + 1) * n * 4.0;
   }
   if (host_stats[3]) {
+    if (build == 2 && (h_stats[4] & 8ull) && !(h_stats[4] & 7ull)) return kWhashOverflow;  // a warp table filled up: the caller redoes the call
     set_error("pair_counts: %llu failures (tile could not be split further, or watchdog code %llu)", host_stats[3], h_stats[4]);
     return KMSC_E_STATE;
   }
@@ -1066,7 +1133,7 @@ __global__ void place_block_kernel(const unsigned long long* __restrict__ T, int
 }
 
 static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
-                               const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W);
+                               const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W, bool no_whash = false);
 
 // Core: d_W (n*n u64, device) is zeroed and filled. Synchronous at return.
 // One kernel pass holds the membership of up to 256 sets (the accumulator tile of the Gram).
@@ -1108,7 +1175,7 @@ int pair_counts_run(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
 }
 
 static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
-                               const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W) {
+                               const int32_t* bucket_ids, int32_t n_ids, unsigned long long* d_W, bool no_whash) {
   const kmsc_set* s0 = sets[0];
   if (!s0) { set_error("sets[0] is NULL"); return KMSC_E_INVALID; }
   int64_t total_keys = 0;
@@ -1208,7 +1275,7 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
       if ((rank++ & 63) == 21) probe[b >> 5] |= 1u << (b & 31);
       else rest[b >> 5] |= 1u << (b & 31);
     }
-    KMSC_TRY(run_phase(ctx, sets, n, ns, false, probe.data(), L_cons, mean_bucket, d_W, st));
+    KMSC_TRY(run_phase(ctx, sets, n, ns, 0, probe.data(), L_cons, mean_bucket, d_W, st));
     if (st[1] > 0) rho = (double)st[0] / (double)st[1];
     ctx->pc_last_stats[0] += st[0]; ctx->pc_last_stats[1] += st[1]; ctx->pc_last_stats[2] += st[2];
     phase2 = rest.data();
@@ -1223,11 +1290,24 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
   // pair_counts_stream.cuh): break-even near rho = 14 ns / 64.
   // KMSC_P3_BUILD=hash|merge overrides (tests run both).
   bool merge_build = ns <= 128 && rho >= 14.0 * (ns / 64);
+  // warp-private hash tables (pair_counts_whash.cuh): every lane inserts its own key, no shared
+  // atomics on the hot path; tables sized by the distinct keys of a segment, so related sets only.
+  // Measured r02u on C2: 6.3 ms against 3.07 ms for the merge build (a CTA-wide flush per 2 K distinct
+  // keys), so it is never chosen by the library; KMSC_P3_BUILD=whash keeps it under the parity tests.
+  bool whash_build = false;
   if (const char* e = getenv("KMSC_P3_BUILD")) {
-    if (!strcmp(e, "hash")) merge_build = false;
-    else if (!strcmp(e, "merge")) merge_build = ns <= 128;
+    if (!strcmp(e, "hash")) { merge_build = false; whash_build = false; }
+    else if (!strcmp(e, "merge")) { merge_build = ns <= 128; whash_build = false; }
+    else if (!strcmp(e, "whash")) whash_build = ns == 64 && !no_whash;
   }
-  if (merge_build) {
+  if (whash_build) {
+    // tiles of several table fills of all warps; the kernel cuts them into segments
+    const double r = rho > 1.0 ? rho : 1.0;
+    double fills = 16.0;
+    if (const char* e = getenv("KMSC_P3_FILLS")) { const double v = atof(e); if (v > 0.1 && v < 256) fills = v; }
+    L = (unsigned long long)(fills * r * (WhCfg<64>::TS / 4) * (WhCfg<64>::T / 32));
+    if (L < L_cons) L = L_cons;
+  } else if (merge_build) {
     // no table to overflow (a full mask arena is flushed and the merge resumes): tiles of a few
     // arena fills keep the per-set slices long (less block over-read at their ends) and amortise
     // the end-of-tile imbalance between the warps
@@ -1238,8 +1318,14 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
     if (L < L_cons) L = L_cons;
   }
   if (L > L_max) L = L_max;
-  ctx->pc_last_build = merge_build ? 1 : 0;
-  KMSC_TRY(run_phase(ctx, sets, n, ns, merge_build, phase2, L, mean_bucket, d_W, st));
+  const int build = whash_build ? 2 : merge_build ? 1 : 0;
+  ctx->pc_last_build = build;
+  {
+    const int rho_q = std::max(1, (int)(0.75 * (rho > 1.0 ? rho : 1.0)));
+    const int rc = run_phase(ctx, sets, n, ns, build, phase2, L, mean_bucket, d_W, st, rho_q);
+    if (rc == kWhashOverflow) return pair_counts_run_256(ctx, sets, n, bucket_ids, n_ids, d_W, true);  // from scratch, without this build
+    if (rc != KMSC_OK) return rc;
+  }
   if (st[1] > 0) {
     ctx->pc_rho = (double)st[0] / (double)st[1];
     ctx->pc_rho_n = n;

@@ -33,7 +33,7 @@ constexpr int kSortThreads = 256; // sort kernel
 constexpr int kMaxB1 = 13;        // bins of the first level: at most 8192
 constexpr int kMaxSub = 13;       // sub-bins per partition: at most 8192
 constexpr int kLongRun = 24;      // sub-bin runs longer than this are sorted by the whole CTA
-constexpr int kLongCap = 512;     // such runs per partition (beyond: the owning thread heap-sorts)
+constexpr int kLongCap = 128;     // such runs per partition (beyond: the owning thread heap-sorts); 1 KB: three CTAs fit an SM
 
 struct Job {
   const unsigned long long* words;  // 2-bit codes, 32 per word, first base in the top bits

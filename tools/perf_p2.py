@@ -37,6 +37,21 @@ def call():
     return ctx.sets_from_packed_batch(K, N, KB, None, [str_offs] * n_sets, words_ptrs=[h.data_ptr() for h in pinned])
 
 
+if os.environ.get("CHECK") == "1":
+    # the staged sort against the general pipeline on the same input: sizes and XOR hashes
+    ss = call()
+    os.environ["KMSC_P2_LEGACY"] = "1"
+    for i, h in enumerate(pinned[:4]):
+        ref = ctx.set_from_packed(K, N, KB, None, str_offs, words_ptr=h.data_ptr())
+        assert (ref.n_keys, ref.Hash()) == (ss[i].n_keys, ss[i].Hash()), f"set {i}: staged sort and general pipeline differ"
+        a, b = ref.to_csr(), ss[i].to_csr()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        ref.free()
+    del os.environ["KMSC_P2_LEGACY"]
+    print(f"CHECK ok: {n_sets} x {kmers}, first sets identical to the general pipeline", flush=True)
+    for s in ss:
+        s.free()
+
 if once:
     ss = call()
     torch.cuda.synchronize()
