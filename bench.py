@@ -924,7 +924,7 @@ def main():
     # DRAM traffic of the dominant kernel per launch: from the committed ncu capture of this
     # workload (it cannot be measured outside a profiler); null for any other shape
     traffic = None
-    kernel_name = "pair_counts_stream_kernel" if p3_build == 1 else "pair_counts_kernel"
+    kernel_name = {1: "pair_counts_stream_kernel", 3: "pair_counts_lane_kernel"}.get(p3_build, "pair_counts_kernel")
     try:
         tr = json.loads((ROOT / "profiles" / "p3_traffic.json").read_text())["kernels"][kernel_name]
         if args.sets == 64 and args.kmers == 10_000_000 and K == 23:
@@ -932,7 +932,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kernel_name,
-                "build": "warp-wide multiway merge (related sets)" if p3_build == 1 else "shared-memory hash table",
+                "build": {1: "warp-wide multiway merge (related sets)", 3: "lane-private tables (one fine bucket per lane)"}.get(p3_build, "shared-memory hash table"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",

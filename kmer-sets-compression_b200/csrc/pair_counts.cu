@@ -781,6 +781,7 @@ pair_counts_kernel(const SetDesc* __restrict__ sets, int n_sets, int spw, const 
 }  // namespace kmsc
 #include "pair_counts_stream.cuh"
 #include "pair_counts_whash.cuh"
+#include "pair_counts_lane.cuh"
 namespace kmsc {
 
 // ---------------------------------------------------------------------------
@@ -973,6 +974,126 @@ static int launch_main_ns(kmsc_ctx* ctx, int ns, const SetDesc* d_sets, int n_se
     case 128: return launch_main<KeyT, 128>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
     default: return launch_main<KeyT, 256>(ctx, d_sets, n_sets, d_offsT, d_tiles, d_ntiles, d_counter, d_W, d_stats, key_bits, fine_level, max_tiles);
   }
+}
+
+
+// ---------------------------------------------------------------------------
+// the lane build (pair_counts_lane.cuh): n <= 64 sets, 2- / 4-byte keys, no planning pass
+// ---------------------------------------------------------------------------
+constexpr int kLaneTarget = 42;   // mean distinct keys per row the 64-slot lane tables are run at
+
+// The level whose rows hold <= kLaneTarget distinct keys on average (rho = keys per distinct key), or -1.
+// 4-byte keys that use all 32 bits need f >= 1: the table key (the key without the row's f bits) must
+// never be the empty marker.
+static int lane_level(const kmsc_set* s0, double total_keys, double rho, int nb_live, bool forced) {
+  if (s0->key_bytes > 4) return -1;
+  const int f_min = (s0->key_bytes == 4 && s0->key_bits >= 32) ? 1 : 0;
+  if (f_min > s0->max_level) return -1;
+  const double distinct = total_keys / (rho > 1.0 ? rho : 1.0);
+  for (int f = f_min; f <= s0->max_level; f++)
+    if (distinct / ((double)nb_live * (double)(1 << f)) <= (double)kLaneTarget) return f;
+  return forced ? s0->max_level : -1;
+}
+
+template <typename KeyT>
+static int launch_lane(kmsc_ctx* ctx, const SetDesc* d_sets, int n_sets, int f, uint32_t NF, uint32_t row_lo,
+                       uint32_t row_hi, const uint32_t* d_bitmap, int tbits, float inv_rho, uint32_t* d_counter,
+                       unsigned long long* d_W, unsigned long long* d_stats, uint2* d_retry,
+                       uint32_t* d_retry_count, uint32_t retry_cap) {
+  auto kern = pair_counts_lane_kernel<KeyT>;
+  static bool attr_set[64] = {false};
+  if (ctx->device >= 64 || !attr_set[ctx->device]) {
+    KMSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LnLayout::total));
+    if (getenv("KMSC_DEBUG")) {
+      cudaFuncAttributes fa;
+      KMSC_CUDA(cudaFuncGetAttributes(&fa, kern));
+      fprintf(stderr, "[kmsc] pair_counts lane T=%d smem=%zu regs=%d\n", LnCfg::T, (size_t)LnLayout::total, fa.numRegs);
+    }
+    if (ctx->device < 64) attr_set[ctx->device] = true;
+  }
+  const long long chunks = ((long long)(row_hi - (row_lo & ~31u)) + 31) / 32;
+  long long grid = std::min<long long>(ctx->sm_count, (chunks + LnCfg::NW - 1) / LnCfg::NW);
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, LnCfg::T, LnLayout::total, ctx->stream>>>(d_sets, n_sets, f, NF, row_lo, row_hi, d_bitmap,
+                                                                  tbits, inv_rho, d_counter, d_W, d_stats, d_retry,
+                                                                  d_retry_count, retry_cap);
+  pair_counts_lane_retry_kernel<KeyT><<<ctx->sm_count, 128, 0, ctx->stream>>>(d_sets, n_sets, NF, tbits, d_retry,
+                                                                             d_retry_count, retry_cap, d_W, d_stats);
+  count_launch(ctx, 2);
+  KMSC_CUDA(cudaGetLastError());
+  return KMSC_OK;
+}
+
+constexpr int kLaneRedo = 1001;  // internal: the retry list filled up, redo the call with another build
+
+// One pass of the lane build over the buckets selected by h_bitmap (NULL = all) at level f.
+static int run_phase_lane(kmsc_ctx* ctx, const kmsc_set* const* sets, int n, int f, double rho, const uint32_t* h_bitmap,
+                          unsigned long long* d_W, unsigned long long host_stats[4]) {
+  const kmsc_set* s0 = sets[0];
+  for (int i = 0; i < n; i++) KMSC_TRY(set_ensure_levels(ctx, sets[i]));
+  const int nb = 1 << s0->N;
+  const uint32_t NF = (uint32_t)nb << f;
+  const size_t sz_desc = ((size_t)n * sizeof(SetDesc) + 15) & ~(size_t)15;
+  const size_t sz_bitmap = (size_t)((nb + 31) / 32) * 4;
+  KMSC_TRY(ctx->small.reserve(256 + sz_desc + sz_bitmap + 64));
+  unsigned char* sm = (unsigned char*)ctx->small.p;
+  uint32_t* d_counter = (uint32_t*)(sm + 4);
+  uint32_t* d_retry_count = (uint32_t*)(sm + 8);
+  unsigned long long* d_stats = (unsigned long long*)(sm + 64);
+  SetDesc* d_sets = (SetDesc*)(sm + 256);
+  uint32_t* d_bitmap = h_bitmap ? (uint32_t*)(sm + 256 + sz_desc) : nullptr;
+  const uint32_t retry_cap = std::max<uint32_t>(4096u, NF / 4u);
+  KMSC_TRY(ctx->plan.reserve((size_t)retry_cap * 8));
+  uint2* d_retry = (uint2*)ctx->plan.p;
+
+  void* pin = nullptr;
+  KMSC_TRY(ctx_pinned(ctx, sz_desc + sz_bitmap + 64, &pin));
+  SetDesc* h_sets = (SetDesc*)pin;
+  for (int i = 0; i < n; i++) { h_sets[i].keys = sets[i]->keys; h_sets[i].lev = sets[i]->lev[f]; h_sets[i].lev_finest = sets[i]->lev[sets[i]->max_level]; }
+  KMSC_CUDA(cudaMemsetAsync(sm, 0, 256, ctx->stream));
+  KMSC_CUDA(cudaMemcpyAsync(d_sets, h_sets, sz_desc, cudaMemcpyHostToDevice, ctx->stream));
+  if (h_bitmap) {
+    uint32_t* pb = (uint32_t*)((unsigned char*)pin + sz_desc);
+    memcpy(pb, h_bitmap, sz_bitmap);
+    KMSC_CUDA(cudaMemcpyAsync(d_bitmap, pb, sz_bitmap, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  for (int i = 0; i < 3; i++)
+    if (!ctx->pc_ev[i]) KMSC_CUDA(cudaEventCreate(&ctx->pc_ev[i]));
+  int span_lo = nb, span_hi = 0;
+  for (int i = 0; i < n; i++) {
+    span_lo = std::min(span_lo, sets[i]->b_lo < 0 ? 0 : sets[i]->b_lo);
+    span_hi = std::max(span_hi, sets[i]->b_hi < 0 ? nb : sets[i]->b_hi);
+  }
+  if (span_lo >= span_hi) { span_lo = 0; span_hi = nb; }
+  const uint32_t row_lo = (uint32_t)span_lo << f, row_hi = (uint32_t)span_hi << f;
+  const int tbits = s0->key_bits - f;   // bits of a table key
+  const float inv_rho = (float)(1.0 / (rho > 1.0 ? rho : 1.0));
+  KMSC_CUDA(cudaEventRecord(ctx->pc_ev[1], ctx->stream));
+  int rc;
+  if (s0->key_bytes == 2)
+    rc = launch_lane<uint16_t>(ctx, d_sets, n, f, NF, row_lo, row_hi, d_bitmap, tbits, inv_rho, d_counter, d_W, d_stats, d_retry, d_retry_count, retry_cap);
+  else
+    rc = launch_lane<uint32_t>(ctx, d_sets, n, f, NF, row_lo, row_hi, d_bitmap, tbits, inv_rho, d_counter, d_W, d_stats, d_retry, d_retry_count, retry_cap);
+  if (rc != KMSC_OK) return rc;
+  KMSC_CUDA(cudaEventRecord(ctx->pc_ev[2], ctx->stream));
+  unsigned long long* h_stats = (unsigned long long*)((unsigned char*)pin + sz_desc + sz_bitmap);
+  KMSC_CUDA(cudaMemcpyAsync(h_stats, d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 4; i++) host_stats[i] = h_stats[i];
+  {
+    float ms_main = 0;
+    KMSC_CUDA(cudaEventElapsedTime(&ms_main, ctx->pc_ev[1], ctx->pc_ev[2]));
+    ctx->pc_main_ms += ms_main;
+    ctx->pc_main_launches += 1;
+    // every key once + one offset per (row, set) at level f + the bucket-level rows of the formula
+    ctx->pc_algo_bytes += (double)h_stats[0] * s0->key_bytes + (double)(nb + 1) * n * 4.0;
+  }
+  if (h_stats[4] & 16ull) return kLaneRedo;
+  if (host_stats[3]) {
+    set_error("pair_counts (lane build): %llu failures (watchdog code %llu)", host_stats[3], h_stats[4]);
+    return KMSC_E_STATE;
+  }
+  return KMSC_OK;
 }
 
 constexpr int kWhashOverflow = 1000;  // internal: run_phase's "redo with another build"
@@ -1295,10 +1416,38 @@ static int pair_counts_run_256(kmsc_ctx* ctx, const kmsc_set* const* sets, int32
   // Measured r02u on C2: 6.3 ms against 3.07 ms for the merge build (a CTA-wide flush per 2 K distinct
   // keys), so it is never chosen by the library; KMSC_P3_BUILD=whash keeps it under the parity tests.
   bool whash_build = false;
+  // lane-private tables (pair_counts_lane.cuh): one fine bucket (or a 1 / 2^q part of it) per lane, no bank
+  // conflicts, no atomics, no compaction pass. Measured r02w on C2: 7.0 ms against 3.08 ms for the merge
+  // build -- the 32 runs a warp walks per set differ in length (Poisson, ~10 keys), so 38 % of the lanes
+  // work per iteration (ncu: 3.2e9 warp instructions, 43 % issue utilisation at 8 warps per SM). Never
+  // chosen by the library; KMSC_P3_BUILD=lane keeps it under the parity tests.
+  int lane_f = -1;
+  bool lane_build = false;
   if (const char* e = getenv("KMSC_P3_BUILD")) {
-    if (!strcmp(e, "hash")) { merge_build = false; whash_build = false; }
-    else if (!strcmp(e, "merge")) { merge_build = ns <= 128; whash_build = false; }
-    else if (!strcmp(e, "whash")) whash_build = ns == 64 && !no_whash;
+    if (!strcmp(e, "hash")) { merge_build = false; whash_build = false; lane_build = false; }
+    else if (!strcmp(e, "merge")) { merge_build = ns <= 128; whash_build = false; lane_build = false; }
+    else if (!strcmp(e, "whash")) { whash_build = ns == 64 && !no_whash; lane_build = false; }
+    else if (!strcmp(e, "lane")) {
+      lane_build = false;
+      if (ns == 64 && !no_whash) {
+        lane_f = lane_level(s0, (double)total_keys, rho, nb_live, true);
+        lane_build = lane_f >= 0;
+      }
+    }
+  }
+  if (lane_build) {
+    ctx->pc_last_build = 3;
+    const int rc = run_phase_lane(ctx, sets, n, lane_f, rho, phase2, d_W, st);
+    if (rc == kLaneRedo) return pair_counts_run_256(ctx, sets, n, bucket_ids, n_ids, d_W, true);  // from scratch, without this build
+    if (rc != KMSC_OK) return rc;
+    if (st[1] > 0) {
+      ctx->pc_rho = (double)st[0] / (double)st[1];
+      ctx->pc_rho_n = n;
+      ctx->pc_rho_k = s0->K;
+    }
+    ctx->pc_last_stats[0] += st[0]; ctx->pc_last_stats[1] += st[1]; ctx->pc_last_stats[2] += st[2];
+    ctx->pc_last_L = (unsigned long long)lane_f;
+    return KMSC_OK;
   }
   if (whash_build) {
     // tiles of several table fills of all warps; the kernel cuts them into segments

@@ -73,11 +73,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// bounded wait (a watchdog against protocol bugs): false if the phase did not complete
-__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t max_tries = 1u << 18) {
-  for (uint32_t i = 0; i < max_tries; i++)
-    if (mbar_try_wait(bar, parity)) return true;
-  return false;
+// bounded wait (a watchdog against protocol bugs): false if the phase did not complete within
+// ~2^32 SM clocks (about two seconds). Bounded by the clock, not by a poll count: under a profiler,
+// MPS or preemption a slow-but-correct MMA must not turn into an error.
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > (1ll << 32)) return false;
+  return true;
 }
 
 // ---- descriptors ------------------------------------------------------------------------------

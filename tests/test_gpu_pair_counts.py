@@ -22,11 +22,12 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(autouse=True, params=["hash", "merge", "whash"])
+@pytest.fixture(autouse=True, params=["hash", "merge", "whash", "lane"])
 def build(request, monkeypatch):
     """every case runs with all builds of the main kernel (KMSC_P3_BUILD): the CTA-wide hash table,
-    the warp-wide multiway merge and the warp-private hash tables give the same matrices (whash takes
-    up to 64 sets and hands a call whose tables fill up back to the other builds)"""
+    the warp-wide multiway merge, the warp-private hash tables and the lane-private tables give the same
+    matrices (whash and lane take up to 64 sets; whash hands a call whose tables fill up back to the other
+    builds, lane sends the rows that outgrow a table through its retry kernel)"""
     monkeypatch.setenv("KMSC_P3_BUILD", request.param)
     return request.param
 
@@ -47,7 +48,8 @@ def _check(ctx, oracle, kmer_sets, K, N, kb, bucket_ids=None):
     got, visits = ctx.pair_counts(dev, bucket_ids, with_visits=True)
     import os
     if any(len(k) for k in kmer_sets):
-        want_build = {"merge": 1 if len(kmer_sets) <= 128 else 0, "whash": 2 if len(kmer_sets) <= 64 else None, "hash": 0}[os.environ["KMSC_P3_BUILD"]]
+        want_build = {"merge": 1 if len(kmer_sets) <= 128 else 0, "whash": 2 if len(kmer_sets) <= 64 else None, "hash": 0,
+                      "lane": 3 if len(kmer_sets) <= 64 and kb <= 4 else None}[os.environ["KMSC_P3_BUILD"]]
         if want_build is not None:
             assert ctx.pair_counts_build() in ((want_build,) if want_build != 2 else (2, 1, 0))   # whash may hand over on overflow
     want, want_visits = oracle.pair_counts(offs_l, keys_l, kb, 1 << N, bucket_ids=bucket_ids, n_threads=8)
