@@ -160,6 +160,21 @@ int kmsc_sets_from_packed_batch(kmsc_ctx* ctx, int K, int N, int key_bytes, int3
  * (lib/core/spss.h:230-615, 1039-1858) by one device binary search per neighbour. */
 int kmsc_set_neighbors(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int32_t* out);
 
+/* SPSS construction on the device. Replaces GetSPSS / GetSPSSCanonical
+ * (lib/core/spss.h:230-615 unitigs, :1039-1858 greedy path cover) and with them
+ * KmerSetCompact::FromKmerSet (lib/core/kmer_set_compact.h:89-100, lib/core/spss.h:1836-1858): a set of
+ * strings that spells every k-mer of the set exactly once (canonical != 0: it or its reverse complement),
+ * the property the reference's tests check (test/spss.cc:57-68, 113-124). Every k-mer port (left / right
+ * end) is linked to at most one neighbouring port by `rounds` rounds of mutual proposals (<= 0: 8; round
+ * one joins exactly the unitig ends, later rounds stitch unitigs like the reference's path cover), the
+ * resulting paths are ranked by pointer jumping, cycles are cut at their smallest k-mer. Strings are
+ * ordered by their first k-mer's position in the set; the output is deterministic for a given set.
+ * kmsc_spss_build leaves the text on the device and reports its size; kmsc_spss_fetch copies the result
+ * of the LAST build of this context: text (n_chars bytes, no separators) and str_offs (n_strings + 1). */
+int kmsc_spss_build(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int rounds, int64_t* n_strings,
+                    int64_t* n_chars);
+int kmsc_spss_fetch(kmsc_ctx* ctx, char* text, int64_t* str_offs);
+
 /* ---- P3: all-pairs intersection counts ------------------------------------------ */
 /* Replaces GetEdgeWeight and the initial all-pairs loop of KmerSetSet's
  * constructor (lib/core/kmer_set_set.h:158-219): out[i*n + j] =

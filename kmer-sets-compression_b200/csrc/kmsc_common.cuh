@@ -61,6 +61,8 @@ struct kmsc_ctx {
   kmsc::Scratch work3;
   kmsc::Scratch stage;    // input staging (text, packed bases)
   kmsc::Scratch small;    // small per-call device arrays (descriptors, ids)
+  kmsc::Scratch spss_out; // result of the last kmsc_spss_build: text, then string offsets
+  int64_t spss_strings = 0, spss_chars = 0;
   // staged partition sort: up to kP2Slots groups of jobs in flight, each with its own tables
   static constexpr int kP2Slots = 4;
   kmsc::Scratch p2a[kP2Slots];      // job table, bin bases, cursors

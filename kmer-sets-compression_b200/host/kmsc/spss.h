@@ -2,13 +2,10 @@
 //
 //  * GetKmerSetFromSPSS: the decode (reference lib/core/spss.h:1861-1941) runs on the
 //    GPU through kmsc_set_from_spss (P2).
-//  * GetSPSS / GetSPSSCanonical: construction (reference lib/core/spss.h:230-1858) is a
-//    "next" row and stays on the host. The reference builds unitigs and then
-//    a greedy path cover; any output that spells every k-mer of the set exactly once is
-//    valid (test/spss.cc:57-68, 113-124). This builder asks the GPU for the de Bruijn
-//    neighbours of every k-mer (kmsc_set_neighbors: one binary search per neighbour, the
-//    Contains() calls that dominate the reference) and walks greedy simplitigs over that
-//    table on the host. Output is deterministic for a given set.
+//  * GetSPSS / GetSPSSCanonical: construction (reference lib/core/spss.h:230-1858) runs on the
+//    GPU as well (kmsc_spss_build, csrc/spss.cu: port matching + pointer jumping). The reference
+//    builds unitigs and then a greedy path cover; any output that spells every k-mer of the set
+//    exactly once is valid (test/spss.cc:57-68, 113-124). Output is deterministic for a given set.
 #ifndef KMSC_HOST_SPSS_H_
 #define KMSC_HOST_SPSS_H_
 #include <algorithm>
@@ -21,14 +18,6 @@
 
 namespace kmsc {
 
-namespace internal {
-// index of value v in the sorted array, or -1
-inline std::int64_t FindSorted(const std::vector<std::uint64_t>& a, std::uint64_t v) {
-  auto it = std::lower_bound(a.begin(), a.end(), v);
-  return (it != a.end() && *it == v) ? static_cast<std::int64_t>(it - a.begin()) : -1;
-}
-}  // namespace internal
-
 // Complement of a string (reverse + A<->T, C<->G), reference spss.h:20-45.
 inline std::string Complement(std::string s) {
   std::reverse(s.begin(), s.end());
@@ -36,67 +25,26 @@ inline std::string Complement(std::string s) {
   return s;
 }
 
-// Greedy simplitigs over the device-computed neighbour table (kmsc_set_neighbors): start at an
-// unvisited k-mer, extend right while an unvisited successor exists (bases tried in A, C, G, T
-// order), then left. The walk keeps (k-mer index, orientation): orientation 1 means the string
-// spells the reverse complement of the stored (canonical) k-mer, whose successors are the
-// complemented predecessors of the stored one. Output is deterministic for a given set.
+// The strings of a device-built SPSS (kmsc_spss_build + kmsc_spss_fetch): the text comes back as one
+// buffer and is cut at the string offsets.
 template <int K, int N, typename KeyType>
 std::vector<std::string> BuildSPSS(const KmerSet<K, N, KeyType>& kmer_set, bool canonical) {
-  const std::vector<std::uint64_t>& a = kmer_set.SortedBits();
-  const std::size_t n = a.size();
   std::vector<std::string> out;
-  if (n == 0) return out;
-  std::vector<std::int32_t> nb(n * 8);
+  if (kmer_set.Size() == 0) return out;
+  std::int64_t n_strings = 0, n_chars = 0;
+  std::string text;
+  std::vector<std::int64_t> offs;
   {
     const SetPtr dev = kmer_set.Dev();
     std::lock_guard<std::mutex> l(Device::Mu());
-    Device::Check(kmsc_set_neighbors(Device::Ctx(), dev->set, canonical ? 1 : 0, nb.data()), "kmsc_set_neighbors");
+    Device::Check(kmsc_spss_build(Device::Ctx(), dev->set, canonical ? 1 : 0, /*rounds=*/0, &n_strings, &n_chars), "kmsc_spss_build");
+    text.resize(static_cast<std::size_t>(n_chars));
+    offs.resize(static_cast<std::size_t>(n_strings) + 1);
+    Device::Check(kmsc_spss_fetch(Device::Ctx(), text.data(), offs.data()), "kmsc_spss_fetch");
   }
-  std::vector<bool> visited(n, false);
-  // oriented neighbour of (i, o) when base c is appended (right = true) or prepended
-  auto step = [&](std::size_t i, int o, int c, bool right, std::size_t* j, int* o2) -> bool {
-    std::int32_t e;
-    if (o == 0) e = nb[i * 8 + (right ? 0 : 4) + static_cast<std::size_t>(c)];
-    else e = nb[i * 8 + (right ? 4 : 0) + static_cast<std::size_t>(3 - c)];
-    if (e < 0) return false;
-    *j = static_cast<std::size_t>(e >> 1);
-    *o2 = o == 0 ? (e & 1) : !(e & 1);
-    return true;
-  };
-  std::string left;  // bases prepended while walking left (reversed)
-  for (std::size_t start = 0; start < n; start++) {
-    if (visited[start]) continue;
-    visited[start] = true;
-    std::string s = Kmer<K>(a[start]).String();
-    for (int dir = 0; dir < 2; dir++) {
-      const bool right = dir == 0;
-      left.clear();
-      std::size_t cur = start;
-      int o = 0;
-      for (;;) {
-        bool moved = false;
-        for (int c = 0; c < 4; c++) {
-          std::size_t j;
-          int o2;
-          if (step(cur, o, c, right, &j, &o2) && !visited[j]) {
-            visited[j] = true;
-            (right ? s : left).push_back("ACGT"[c]);
-            cur = j;
-            o = o2;
-            moved = true;
-            break;
-          }
-        }
-        if (!moved) break;
-      }
-    }
-    if (!left.empty()) {
-      std::reverse(left.begin(), left.end());
-      s = left + s;
-    }
-    out.push_back(std::move(s));
-  }
+  out.reserve(static_cast<std::size_t>(n_strings));
+  for (std::int64_t i = 0; i < n_strings; i++)
+    out.emplace_back(text, static_cast<std::size_t>(offs[i]), static_cast<std::size_t>(offs[i + 1] - offs[i]));
   return out;
 }
 

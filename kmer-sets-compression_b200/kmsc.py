@@ -30,7 +30,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_spss_build", "kmsc_spss_fetch", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
@@ -118,6 +118,8 @@ def lib() -> C.CDLL:
     L.kmsc_count_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     L.kmsc_count_last_counts.argtypes = [C.c_void_p, _u8p, C.c_int64]
     L.kmsc_set_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+    L.kmsc_spss_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.kmsc_spss_fetch.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
     L.kmsc_set_bucket_offsets.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, _i64p]
     L.kmsc_set_export_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.kmsc_set_import_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -331,6 +333,18 @@ class Context:
         out = np.zeros((max(1, s.n_keys), 8), np.int32)
         _check(lib().kmsc_set_neighbors(self.h, s.h, int(canonical), out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out[: s.n_keys]
+
+    def spss_build(self, s: DeviceSet, canonical=True, rounds=0, fetch=True):
+        """SPSS of a set, built on the device: list of strings (fetch=False: just (n_strings, n_chars))"""
+        ns, nc = C.c_int64(0), C.c_int64(0)
+        _check(lib().kmsc_spss_build(self.h, s.h, int(canonical), int(rounds), C.byref(ns), C.byref(nc)))
+        if not fetch:
+            return ns.value, nc.value
+        text = C.create_string_buffer(max(1, nc.value))
+        offs = np.zeros(ns.value + 1, np.int64)
+        _check(lib().kmsc_spss_fetch(self.h, text, offs.ctypes.data_as(_i64p)))
+        raw = text.raw
+        return [raw[offs[i]:offs[i + 1]].decode() for i in range(ns.value)]
 
     # -- multi-GPU inside the library -----------------------------------------------------------
     @staticmethod
