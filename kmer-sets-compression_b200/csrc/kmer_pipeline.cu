@@ -121,46 +121,118 @@ __global__ void sort_runs_kernel(const KeyT* __restrict__ tmp, const uint32_t* _
   if (dup) *dup_flag = 1u;
 }
 
-// CTA per queued long run: bitonic sort in shared memory (L <= kSmemSortMax);
-// longer runs are re-queued for the host-driven fallback
+// CTA per queued long run (kRankSortMax < L <= kSmemSortMax; counting reads at 90 x coverage puts ~200 k-mer
+// instances of ~60 distinct k-mers into a finest bucket): a counting sort in shared memory over the top
+// kSubBits bits below the fine level -- histogram, scan, grouped copy -- then every key finds its rank
+// inside its sub-bin (a handful of keys: the copies of one k-mer and a neighbour or two) and goes straight
+// to its final place. Equal keys are interchangeable, so the order among them is whatever the grouped copy
+// left. A sub-bin longer than kSubRankMax (a k-mer with hundreds of copies next to others) sends the run
+// through the bitonic network instead; longer runs are re-queued for the host-driven fallback.
+constexpr int kSubBits = 10;
+constexpr int kSubRankMax = 96;
+
 template <typename KeyT>
-__global__ void sort_big_kernel(const KeyT* __restrict__ tmp, const uint32_t* __restrict__ offs,
-                                KeyT* __restrict__ out, const uint32_t* __restrict__ big_list,
-                                const uint32_t* __restrict__ big_count, uint32_t* __restrict__ huge_list,
-                                uint32_t* __restrict__ huge_count, uint32_t* __restrict__ dup_flag) {
-  __shared__ KeyT sk[kSmemSortMax];
+__global__ void __launch_bounds__(256)
+sort_big_kernel(const KeyT* __restrict__ tmp, const uint32_t* __restrict__ offs,
+                KeyT* __restrict__ out, const uint32_t* __restrict__ big_list,
+                const uint32_t* __restrict__ big_count, uint32_t* __restrict__ huge_list,
+                uint32_t* __restrict__ huge_count, uint32_t* __restrict__ dup_flag, int rem_bits) {
+  extern __shared__ __align__(16) unsigned char sort_big_smem[];
+  KeyT* sk = reinterpret_cast<KeyT*>(sort_big_smem);                     // the run as loaded
+  KeyT* sg = sk + kSmemSortMax;                                          // grouped by sub-bin
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(sg + kSmemSortMax);        // [2^kSubBits + 1] counts -> starts
+  uint32_t* cur = cnt + (1 << kSubBits) + 1;                             // [2^kSubBits] fill cursors
+  __shared__ uint32_t s_wsum[8];
+  __shared__ int s_long, s_dup;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int shift = rem_bits > kSubBits ? rem_bits - kSubBits : 0;
+  const uint32_t bmask = (1u << kSubBits) - 1u;
   const uint32_t nbig = *big_count;
   for (uint32_t t = blockIdx.x; t < nbig; t += gridDim.x) {
     const uint32_t x = big_list[t];
     const uint32_t a = offs[x], L = offs[x + 1] - a;
     if (L > kSmemSortMax) {
-      if (threadIdx.x == 0) huge_list[atomicAdd(huge_count, 1u)] = x;
+      if (tid == 0) huge_list[atomicAdd(huge_count, 1u)] = x;
       continue;
     }
-    uint32_t P = 1;
-    while (P < L) P <<= 1;
-    const KeyT INF = (KeyT)~(KeyT)0;
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sk[i] = i < L ? tmp[a + i] : INF;
+    for (int i = tid; i <= (1 << kSubBits); i += 256) cnt[i] = 0;
+    if (tid == 0) { s_long = 0; s_dup = 0; }
     __syncthreads();
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-          const uint32_t ixj = i ^ j;
-          if (ixj > i) {
-            const KeyT u = sk[i], w = sk[ixj];
-            const bool up = (i & k) == 0;
-            if ((u > w) == up) { sk[i] = w; sk[ixj] = u; }
+    for (uint32_t i = tid; i < L; i += 256) {
+      const KeyT k = tmp[a + i];
+      sk[i] = k;
+      atomicAdd(&cnt[(uint32_t)(k >> shift) & bmask], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the 1024 counts: 4 per thread, warp scan, warp totals
+    {
+      uint32_t v[4], s = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { v[q] = cnt[tid * 4 + q]; s += v[q]; }
+      if (max(max(v[0], v[1]), max(v[2], v[3])) > (uint32_t)kSubRankMax) s_long = 1;
+      uint32_t inc = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (lane == 31) s_wsum[warp] = inc;
+      __syncthreads();
+      uint32_t pre = inc - s;
+      for (int w = 0; w < warp; w++) pre += s_wsum[w];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { cnt[tid * 4 + q] = pre; cur[tid * 4 + q] = pre; pre += v[q]; }
+      if (tid == 255) cnt[1 << kSubBits] = pre;
+    }
+    __syncthreads();
+    if (s_long) {
+      // bitonic network over the padded run (INF padding sorts last; real keys equal to INF are still
+      // among the first L)
+      uint32_t P = 1;
+      while (P < L) P <<= 1;
+      const KeyT INF = (KeyT)~(KeyT)0;
+      for (uint32_t i = L + tid; i < P; i += 256) sk[i] = INF;
+      __syncthreads();
+      for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t i = tid; i < P; i += 256) {
+            const uint32_t ixj = i ^ j;
+            if (ixj > i) {
+              const KeyT u = sk[i], w = sk[ixj];
+              const bool up = (i & k) == 0;
+              if ((u > w) == up) { sk[i] = w; sk[ixj] = u; }
+            }
           }
+          __syncthreads();
         }
-        __syncthreads();
+      }
+      for (uint32_t i = tid; i < L; i += 256) {
+        out[a + i] = sk[i];
+        if (i + 1 < L && sk[i] == sk[i + 1]) s_dup = 1;
+      }
+    } else {
+      for (uint32_t i = tid; i < L; i += 256) {
+        const KeyT k = sk[i];
+        sg[atomicAdd(&cur[(uint32_t)(k >> shift) & bmask], 1u)] = k;
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < L; i += 256) {
+        const KeyT k = sg[i];
+        const uint32_t bin = (uint32_t)(k >> shift) & bmask;
+        const uint32_t b0 = cnt[bin], b1 = cnt[bin + 1];
+        uint32_t r = b0;
+        bool dup = false;
+        for (uint32_t j = b0; j < b1; j++) {
+          const KeyT kj = sg[j];
+          r += (kj < k) || (kj == k && j < i);
+          dup |= kj == k && j != i;
+        }
+        out[a + r] = k;
+        if (dup) s_dup = 1;
       }
     }
-    // INF padding sorts last; real keys equal to INF are still among the first L
-    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) {
-      out[a + i] = sk[i];
-      if (i + 1 < L && sk[i] == sk[i + 1]) *dup_flag = 1u;
-    }
     __syncthreads();
+    if (tid == 0 && s_dup) *dup_flag = 1u;
   }
 }
 
@@ -324,8 +396,14 @@ int pipeline_t(kmsc_ctx* ctx, const PipelineInput& in, const PipelineOptions& op
   } else if (n_occ > 0) {
     scatter_kernel<KeyT><<<pos_blocks, threads, 0, ctx->stream>>>(kp, d_offs, d_aux, d_tmp);
     sort_runs_kernel<KeyT><<<(NF + 127) / 128, 128, 0, ctx->stream>>>(d_tmp, d_offs, NF, d_sorted, d_big, d_ctr + 1, d_ctr + 3);
-    sort_big_kernel<KeyT><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_tmp, d_offs, d_sorted, d_big, d_ctr + 1,
-                                                                     d_huge, d_ctr + 2, d_ctr + 3);
+    {
+      const size_t smem_big = (size_t)2 * kSmemSortMax * sizeof(KeyT) + ((size_t)2 * (1 << kSubBits) + 1) * 4;
+      // (per device, and cheap: set on every call)
+      cudaError_t ea = cudaFuncSetAttribute(sort_big_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+      if (ea != cudaSuccess) return fail(cuda_fail(ea, "sort_big attribute", __FILE__, __LINE__));
+      sort_big_kernel<KeyT><<<ctx->sm_count * 3, 256, smem_big, ctx->stream>>>(d_tmp, d_offs, d_sorted, d_big, d_ctr + 1,
+                                                                              d_huge, d_ctr + 2, d_ctr + 3, kp.fine_shift);
+    }
     count_launch(ctx, 3);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(cuda_fail(e, "pipeline sort", __FILE__, __LINE__));

@@ -18,6 +18,9 @@
 #ifndef KMSC_HOST_KMER_SET_SET_H_
 #define KMSC_HOST_KMER_SET_SET_H_
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <filesystem>
 #include <map>
@@ -107,12 +110,21 @@ class KmerSetSet {
     if (!opt.exact && bucket_ids.empty()) bucket_ids = GetRandomInts((1 << N) / 50, 0, (1 << N) - 1, opt.seed);
     const std::vector<std::int32_t> ids(bucket_ids.begin(), bucket_ids.end());
 
+    // KMSC_TIMING=1: seconds per phase on stderr when the constructor returns
+    const bool timing = std::getenv("KMSC_TIMING") != nullptr;
+    double t_phase[5] = {0, 0, 0, 0, 0};  // decode, weights, split, SPSS re-encode, row re-weights
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(now() - t0).count(); };
+    auto t0 = now();
+
     // resident device sets (the reference re-decodes SPSS on every use)
     std::vector<Set> sets;
     sets.reserve(static_cast<std::size_t>(n0));
     for (const Compact& c : kmer_sets_compact_) sets.push_back(c.ToKmerSet(canonical, n_workers));
+    t_phase[0] = since(t0); t0 = now();
 
     std::vector<std::int64_t> W = PairCounts(sets, opt.exact ? nullptr : &ids);  // dense n x n
+    t_phase[1] = since(t0);
     initial_weights_ = W;
     bucket_ids_ = bucket_ids;
     int n = n0;
@@ -138,14 +150,17 @@ class KmerSetSet {
       if (weight == 0) break;
       merges_.push_back({j, k, weight});
 
+      t0 = now();
       Set inter, jm, km;
       Set::Split(sets[j], sets[k], &inter, &jm, &km, opt.exact ? weight : -1);  // exact weight = |S_j & S_k|
       sets[j] = jm;
       sets[k] = km;
       sets.push_back(inter);
+      t_phase[2] += since(t0); t0 = now();
       kmer_sets_compact_[j] = Compact::FromKmerSet(sets[j], canonical, true, n_workers);
       kmer_sets_compact_[k] = Compact::FromKmerSet(sets[k], canonical, true, n_workers);
       kmer_sets_compact_.push_back(Compact::FromKmerSet(inter, canonical, true, n_workers));
+      t_phase[3] += since(t0); t0 = now();
       children_[j].push_back(n);
       children_[k].push_back(n);
       n += 1;
@@ -164,7 +179,11 @@ class KmerSetSet {
           W2[static_cast<std::size_t>(l) * n + changed[r]] = v;
         }
       W.swap(W2);
+      t_phase[4] += since(t0);
     }
+    if (timing)
+      std::fprintf(stderr, "[kmsc timing] decode %.4f s, initial weights %.4f s, %zu merges: split %.4f s, SPSS re-encode %.4f s, "
+                   "row re-weights %.4f s\n", t_phase[0], t_phase[1], merges_.size(), t_phase[2], t_phase[3], t_phase[4]);
   }
 
   int Size() const { return static_cast<int>(kmer_sets_compact_.size()); }

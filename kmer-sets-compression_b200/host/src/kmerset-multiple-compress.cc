@@ -90,6 +90,13 @@ int Main(const Flags& flags) {
     if (opt.bucket_ids.empty()) { Error("no bucket ids in " + ids_file); return 1; }
   }
   const std::size_t n0 = sets.size();
+  {
+    // the process's first CUDA call (driver + context start-up, 0.5-3 s on an 8-GPU box) is not part of the
+    // constructor: it is logged on its own line
+    const auto t_init = std::chrono::steady_clock::now();
+    Device::Check(kmsc_ctx_sync(Device::Ctx()), "kmsc_ctx_sync");
+    Info("device context ready, seconds = " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count()));
+  }
   const auto t_ctor = std::chrono::steady_clock::now();
   KmerSetSet<K, N, KeyType> kss(std::move(sets), canonical, n_workers, opt);
   Info("constructed kmer_set_set, size = " + std::to_string(kss.Size()) + ", merges = " + std::to_string(kss.Merges().size()) +

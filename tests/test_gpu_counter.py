@@ -77,6 +77,31 @@ def test_fasta_counts_vs_oracle(ctx, oracle, K, N, canonical):
     assert nd2 == len(kmers)
 
 
+@pytest.mark.parametrize("K,N,glen,n_reads", [(9, 10, 30000, 10000), (15, 14, 3000, 3000), (19, 10, 3000, 3000), (31, 14, 2000, 6000)])
+@pytest.mark.parametrize("canonical", [True, False])
+def test_high_coverage_long_runs(ctx, oracle, K, N, glen, n_reads, canonical):
+    """sequencing-read shape (C4): every finest bucket holds 60-4000 k-mer instances -- the copies of a few
+    distinct k-mers. Short k: several distinct k-mers per run (shared-memory counting sort + rank inside the
+    sub-bin); long k over a small genome: a run is the copies of ONE k-mer (sub-bin longer than the rank limit:
+    bitonic network). Counts, saturation and the cutoff against the oracle."""
+    rng = np.random.default_rng(K * 31 + N)
+    base = "".join(rng.choice(list("ACGT"), glen))
+    reads = []
+    for i in range(n_reads):
+        a = int(rng.integers(0, glen - 100))
+        reads.append(base[a:a + 100])
+    kmers, counts = oracle.count_reads(reads, K, canonical)
+    assert counts.max() >= 60
+    data = ("\n".join(reads) + "\n").encode()
+    for cutoff in (1, 40):
+        kept, cut = oracle.counter_to_set(kmers, counts, cutoff)
+        s, gcut, nd = ctx.count_reads(K, N, KB[K], data, canonical=canonical, cutoff=cutoff)
+        assert nd == len(kmers) and gcut == cut
+        assert np.array_equal(s.to_kmers(), kept)
+    for i in rng.integers(0, len(kmers), 40):
+        assert ctx.count_get(int(kmers[i])) == int(counts[i])
+
+
 def test_saturation_at_255(ctx, oracle):  # kmer_counter.h:28-38, test/kmer_counter.cc:12-16
     data = ("ACGTA\n" * 300 + "CCCCC\n" * 255 + "GGGGG\n" * 254).encode()
     s, cut, nd = ctx.count_reads(5, 3, 2, data, canonical=False, cutoff=255)
