@@ -215,7 +215,9 @@ int kmsc_pair_counts_rows(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t n,
 int kmsc_pair_counts_stats(kmsc_ctx* ctx, double* out8);
 /* Which build the main phase of the LAST kmsc_pair_counts* call used: 0 = shared-memory hash
  * table (cost per key), 1 = warp-wide multiway merge (cost per distinct key; chosen for up to
- * 128 related sets). Same results; the environment variable KMSC_P3_BUILD=hash|merge forces one. */
+ * 128 related sets), 2 = warp-private hash tables, 3 = lane-private tables (2 and 3: up to 64 sets,
+ * measured slower, never chosen by the library). Same results; the environment variable
+ * KMSC_P3_BUILD=hash|merge|whash|lane forces one. */
 int kmsc_pair_counts_build(kmsc_ctx* ctx);
 
 /* ---- P4: pair split / set algebra ------------------------------------------------ */
