@@ -287,6 +287,12 @@ int kmsc_codec_encode(kmsc_ctx* ctx, const kmsc_set* set, uint8_t** bytes, int64
 int kmsc_codec_decode(kmsc_ctx* ctx, const uint8_t* bytes, int64_t n_bytes, kmsc_set** out);
 void kmsc_free_host(void* p);
 
+/* Page-locked host buffers for the streaming inputs: a file reader that fills a
+ * buffer obtained here hands kmsc_counter_add_fasta / kmsc_counter_add_reads memory the copy engine reads
+ * directly (the same calls from pageable memory are staged by the driver, several times slower). */
+int kmsc_host_alloc_pinned(size_t bytes, void** out);
+void kmsc_host_free_pinned(void* p);
+
 #ifdef __cplusplus
 }
 #endif

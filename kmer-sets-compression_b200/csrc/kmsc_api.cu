@@ -592,4 +592,14 @@ int kmsc_set_import_range(kmsc_ctx* ctx, int K, int N, int key_bytes, int32_t bu
 
 void kmsc_free_host(void* p) { free(p); }
 
+int kmsc_host_alloc_pinned(size_t bytes, void** out) {
+  if (!out) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  *out = nullptr;
+  KMSC_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return KMSC_OK;
+}
+void kmsc_host_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 }  // extern "C"

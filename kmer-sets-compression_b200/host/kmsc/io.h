@@ -3,8 +3,14 @@
 // error texts. Unlike the reference the file is read in large blocks.
 #ifndef KMSC_HOST_IO_H_
 #define KMSC_HOST_IO_H_
+#include <algorithm>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "kmsc/status.h"
@@ -58,25 +64,35 @@ inline Status ReadRecordChunks(const std::string& file_name, const std::string& 
     if (f == nullptr) return InternalError("failed to open file");
   }
   std::string buf;
-  buf.reserve(chunk_bytes + (1 << 20));
-  std::vector<char> io(1 << 22);
+  buf.reserve(chunk_bytes + (1 << 23));
   Status st = OkStatus();
-  std::size_t lines = 0, scanned = 0, last_even_end = 0;  // state of the newline scan over buf
+  // The cut goes after the last line that closes an even count. Newlines are COUNTED over the new bytes
+  // (std::count vectorises: ~10 GB/s against ~1 GB/s for a byte loop that tracks the position) and the cut
+  // is then found from the end: the last newline if the count is even, the one before it if odd.
+  std::size_t lines = 0, scanned = 0;
   for (;;) {
-    const std::size_t n = std::fread(io.data(), 1, io.size(), f);
-    if (n > 0) buf.append(io.data(), n);
+    const std::size_t old = buf.size();
+    buf.resize(old + (1 << 22));
+    const std::size_t n = std::fread(&buf[old], 1, 1 << 22, f);   // straight into the chunk: no bounce buffer
+    buf.resize(old + n);
     if (buf.size() >= chunk_bytes || n == 0) {
-      for (; scanned < buf.size(); scanned++)
-        if (buf[scanned] == '\n' && (++lines % 2) == 0) last_even_end = scanned + 1;
+      lines += static_cast<std::size_t>(std::count(buf.begin() + static_cast<std::ptrdiff_t>(scanned), buf.end(), '\n'));
+      scanned = buf.size();
       if (n == 0) {
         if (!buf.empty()) st = sink(buf.data(), buf.size());
         break;
       }
-      if (last_even_end > 0) {
-        st = sink(buf.data(), last_even_end);
+      std::size_t cut = 0;   // bytes that end with an even number of lines
+      if (lines >= 2) {
+        std::size_t pos = buf.rfind('\n');
+        if (lines % 2 == 1) pos = buf.rfind('\n', pos - 1);
+        cut = pos + 1;
+      }
+      if (cut > 0) {
+        st = sink(buf.data(), cut);
         if (!st.ok()) break;
-        buf.erase(0, last_even_end);
-        lines = 0; scanned = 0; last_even_end = 0;
+        buf.erase(0, cut);
+        lines = 0; scanned = 0;
       }
     }
   }
@@ -88,6 +104,58 @@ inline Status ReadRecordChunks(const std::string& file_name, const std::string& 
     std::fclose(f);
   }
   return st;
+}
+
+// The same stream with the file side and the consumer overlapped: a reader thread fills
+// chunks (read / decompress, newline scan, cut after whole records) into a queue of at most `depth` chunks
+// while the calling thread hands the previous ones to `sink` (the GPU counter: host-to-device copy + kernels).
+// Chunk boundaries, order and error behaviour are those of ReadRecordChunks; the first failing sink call
+// stops the reader.
+template <typename Sink>
+inline Status ReadRecordChunksOverlapped(const std::string& file_name, const std::string& decompressor,
+                                         std::size_t chunk_bytes, Sink sink, std::size_t depth = 2) {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::string> queue;
+  bool done = false, stop = false;
+  Status reader_status = OkStatus();
+  std::thread reader([&] {
+    Status st = ReadRecordChunks(file_name, decompressor, chunk_bytes, [&](const char* data, std::size_t n) -> Status {
+      std::string chunk(data, n);
+      std::unique_lock<std::mutex> l(mu);
+      cv.wait(l, [&] { return queue.size() < depth || stop; });
+      if (stop) return InternalError("cancelled");
+      queue.push_back(std::move(chunk));
+      cv.notify_all();
+      return OkStatus();
+    });
+    std::lock_guard<std::mutex> l(mu);
+    reader_status = st;
+    done = true;
+    cv.notify_all();
+  });
+  Status st = OkStatus();
+  for (;;) {
+    std::string chunk;
+    {
+      std::unique_lock<std::mutex> l(mu);
+      cv.wait(l, [&] { return !queue.empty() || done; });
+      if (queue.empty()) break;
+      chunk = std::move(queue.front());
+      queue.pop_front();
+      cv.notify_all();
+    }
+    st = sink(chunk.data(), chunk.size());
+    if (!st.ok()) {
+      std::lock_guard<std::mutex> l(mu);
+      stop = true;
+      cv.notify_all();
+      break;
+    }
+  }
+  reader.join();
+  if (!st.ok()) return st;
+  return reader_status;
 }
 
 // std::getline semantics: a trailing '\n' does not open another line.

@@ -6,7 +6,10 @@
 #ifndef KMSC_HOST_KMER_COUNTER_H_
 #define KMSC_HOST_KMER_COUNTER_H_
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <type_traits>
@@ -14,6 +17,7 @@
 #include <vector>
 
 #include "kmsc/io.h"
+#include "kmsc/pinned_reader.h"
 #include "kmsc/kmer_set.h"
 
 namespace kmsc {
@@ -119,13 +123,40 @@ class KmerCounter {
       Device::Check(kmsc_counter_create(Device::Ctx(), K, N, static_cast<int>(sizeof(KeyType)), canonical ? 1 : 0, &c),
                     "kmsc_counter_create");
     }
-    Status st = ReadRecordChunks(file_name, decompressor, chunk_bytes, [&](const char* data, std::size_t n) -> Status {
+    // default: a reader thread freads into page-locked buffers while the device counts the previous chunk;
+    // KMSC_IO_OVERLAP=1: pageable chunks, overlapped; =0: read and count in turn (diagnostics)
+    const char* ov = std::getenv("KMSC_IO_OVERLAP");
+    auto run = [&](auto&& sink) {
+      if (ov && std::atoi(ov) == 0) return ReadRecordChunks(file_name, decompressor, chunk_bytes, sink);
+      if (ov && std::atoi(ov) == 1) return ReadRecordChunksOverlapped(file_name, decompressor, chunk_bytes, sink);
+      return ReadRecordChunksPinned(file_name, decompressor, chunk_bytes, sink);
+    };
+    const bool timing = std::getenv("KMSC_TIMING") != nullptr;
+    if (timing) {   // the process's first CUDA call (context start-up) is kept out of the phase times
+      const auto t_init = std::chrono::steady_clock::now();
       std::lock_guard<std::mutex> l(Device::Mu());
+      Device::Check(kmsc_ctx_sync(Device::Ctx()), "kmsc_ctx_sync");
+      std::fprintf(stderr, "[kmsc timing] device context ready: %.3f s\n",
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count());
+    }
+    const auto t_all = std::chrono::steady_clock::now();
+    double t_dev = 0, t_first = 0;
+    int n_calls = 0;
+    Status st = run([&](const char* data, std::size_t n) -> Status {
+      std::lock_guard<std::mutex> l(Device::Mu());
+      const auto t0 = std::chrono::steady_clock::now();
       const int rc = kmsc_counter_add_fasta(Device::Ctx(), c, data, static_cast<std::int64_t>(n));
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      t_dev += dt;
+      if (n_calls++ == 0) t_first = dt;
       if (rc == KMSC_E_FORMAT) return FailedPreconditionError(kmsc_last_error());
       if (rc != KMSC_OK) return InternalError(kmsc_last_error());
       return OkStatus();
     });
+    if (timing)
+      std::fprintf(stderr, "[kmsc timing] file -> counter: %.3f s in all, %.3f s inside %d kmsc_counter_add_fasta calls (the first, with "
+                   "module loading and allocations: %.3f s)\n",
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_all).count(), t_dev, n_calls, t_first);
     std::lock_guard<std::mutex> l(Device::Mu());
     if (!st.ok()) { kmsc_counter_free(Device::Ctx(), c); return st; }
     kmsc_set* s = nullptr;

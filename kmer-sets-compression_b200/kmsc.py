@@ -33,7 +33,7 @@ EXPORTS = [
     "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_spss_build", "kmsc_spss_fetch", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
-    "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host",
+    "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host", "kmsc_host_alloc_pinned", "kmsc_host_free_pinned",
 ]
 
 

@@ -75,3 +75,38 @@ def test_cli_end_to_end(bins, oracle, tmp_path, K):
     hashes = [int(x) for x in re.findall(r"kmer_set.Hash\(\) = (\d+)", r.stderr)]
     sizes = [int(x) for x in re.findall(r"kmer_set.Size\(\) = (\d+)", r.stderr)]
     assert list(zip(sizes, hashes)) == want
+
+
+def test_build_reader_modes(bins, oracle, tmp_path):
+    """f3: the file side of kmerset-build -- page-locked reader thread (default), pageable overlapped reader,
+    read-and-count in turn, and a piped decompressor -- gives the same set on chunks of a few records; a file
+    with an odd number of lines is refused with the reference's message by every mode"""
+    import os
+    import synth
+    K = 23
+    s = synth.random_genome(9000, 5)
+    txt = synth.to_ascii(s).decode()
+    lines = []
+    for rep in range(3):
+        for a in range(0, len(txt) - 200, 97):
+            lines += [f">r{rep}_{a}", txt[a:a + 211]]
+    fasta = tmp_path / "reads.fa"
+    fasta.write_text("\n".join(lines) + "\n")
+    kmers, counts = oracle.count_reads(lines[1::2], K, True)
+    kept, _ = oracle.counter_to_set(kmers, counts, 2)
+    want = (f"kmer_set.Size() = {len(kept)}", f"kmer_set.Hash() = {oracle.set_hash(kept)}")
+    odd = tmp_path / "odd.fa"
+    odd.write_text("\n".join(lines[:-1]) + "\n")
+    for mode, extra in [(None, []), ("1", []), ("0", []), (None, ["--decompressor=cat"])]:
+        env = dict(os.environ)
+        env.pop("KMSC_IO_OVERLAP", None)
+        if mode is not None:
+            env["KMSC_IO_OVERLAP"] = mode
+        for chunk in (3000, 10_000_000):
+            r = subprocess.run([str(bins / "kmerset-build"), f"--k={K}", "--cutoff=2", f"--chunk_bytes={chunk}", str(fasta)] + extra,
+                               capture_output=True, text=True, timeout=600, env=env)
+            assert r.returncode == 0, r.stderr
+            assert want[0] in r.stderr and want[1] in r.stderr, (mode, extra, chunk, r.stderr[-400:])
+        r = subprocess.run([str(bins / "kmerset-build"), f"--k={K}", "--chunk_bytes=3000", str(odd)] + extra,
+                           capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode != 0 and "even number of lines" in r.stderr, (mode, r.stderr[-300:])
