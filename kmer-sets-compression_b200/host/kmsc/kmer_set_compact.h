@@ -79,6 +79,35 @@ class KmerSetCompact {
     return buckets;
   }
 
+  // every set of a collection in one batched device call (kmsc_sets_from_packed_batch: the host-to-device
+  // copies of later groups overlap the kernels of earlier ones, two synchronisations per group)
+  static std::vector<KmerSet<K, N, KeyType>> ToKmerSetBatch(const std::vector<KmerSetCompact>& compact, bool canonical) {
+    const std::size_t m = compact.size();
+    std::vector<KmerSet<K, N, KeyType>> out;
+    if (m == 0) return out;
+    std::vector<const std::uint64_t*> words(m);
+    std::vector<std::vector<std::int64_t>> offs(m);
+    std::vector<const std::int64_t*> offp(m);
+    std::vector<std::int64_t> nstr(m);
+    for (std::size_t j = 0; j < m; j++) {
+      words[j] = compact[j].words_.data();
+      offs[j] = compact[j].StringOffsets();
+      offp[j] = offs[j].data();
+      nstr[j] = static_cast<std::int64_t>(offs[j].size()) - 1;
+    }
+    std::vector<kmsc_set*> sets(m, nullptr);
+    {
+      std::lock_guard<std::mutex> l(Device::Mu());
+      Device::Check(kmsc_sets_from_packed_batch(Device::Ctx(), K, N, static_cast<int>(sizeof(KeyType)), static_cast<std::int32_t>(m),
+                                                words.data(), offp.data(), nstr.data(), canonical ? 1 : 0, /*dedup=*/1, 0, 1 << N,
+                                                sets.data()),
+                    "kmsc_sets_from_packed_batch");
+    }
+    out.reserve(m);
+    for (kmsc_set* s : sets) out.push_back(KmerSet<K, N, KeyType>(MakeSetPtr(s)));
+    return out;
+  }
+
   // the device set of the k-mers in [bucket_lo, bucket_hi) (a rank's prefix shard)
   KmerSet<K, N, KeyType> ToKmerSetShard(bool canonical, int bucket_lo, int bucket_hi) const {
     return KmerSet<K, N, KeyType>(MakeSetPtr(Decode(canonical, true, bucket_lo, bucket_hi)));

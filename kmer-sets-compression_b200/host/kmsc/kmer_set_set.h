@@ -118,9 +118,7 @@ class KmerSetSet {
     auto t0 = now();
 
     // resident device sets (the reference re-decodes SPSS on every use)
-    std::vector<Set> sets;
-    sets.reserve(static_cast<std::size_t>(n0));
-    for (const Compact& c : kmer_sets_compact_) sets.push_back(c.ToKmerSet(canonical, n_workers));
+    std::vector<Set> sets = Compact::ToKmerSetBatch(kmer_sets_compact_, canonical);   // one batched decode
     t_phase[0] = since(t0); t0 = now();
 
     std::vector<std::int64_t> W = PairCounts(sets, opt.exact ? nullptr : &ids);  // dense n x n

@@ -10,10 +10,13 @@
 // difference sets: what the parity tests compare with the oracle), --gpus=N (mst driver: the
 // k-mer prefix space is sharded over N GPUs of this box, one host thread and one NCCL rank per
 // GPU; the number of sets must be a multiple of N).
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "flags.h"
@@ -31,12 +34,29 @@ int Main(const Flags& flags) {
   const std::string decompressor = flags.Str("decompressor", "");
   const std::vector<std::string>& files = flags.positional;
   std::vector<KmerSetCompact<K, N, KeyType>> sets(files.size());
-  for (std::size_t i = 0; i < files.size(); i++) {
-    Info("loading file: " + files[i]);
-    auto r = KmerSetCompact<K, N, KeyType>::Load(files[i], decompressor);
-    if (!r.ok()) { Error("failed to load file: " + r.status().ToString()); return 1; }
-    sets[i] = std::move(r).value();
+  const auto t_load = std::chrono::steady_clock::now();
+  {
+    // the files are independent: --workers threads read and pack them (the reference loads them in turn)
+    std::vector<std::string> errors(files.size());
+    std::atomic<std::size_t> next{0};
+    auto work = [&] {
+      for (std::size_t i = next++; i < files.size(); i = next++) {
+        auto r = KmerSetCompact<K, N, KeyType>::Load(files[i], decompressor);
+        if (!r.ok()) errors[i] = r.status().ToString();
+        else sets[i] = std::move(r).value();
+      }
+    };
+    std::vector<std::thread> pool;
+    const int n_threads = std::max(1, std::min<int>(n_workers, static_cast<int>(files.size())));
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(work);
+    work();
+    for (std::thread& t : pool) t.join();
+    for (std::size_t i = 0; i < files.size(); i++) {
+      Info("loading file: " + files[i]);
+      if (!errors[i].empty()) { Error("failed to load file: " + errors[i]); return 1; }
+    }
   }
+  const double s_load = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count();
   for (std::size_t i = 0; i < sets.size(); i++)
     Info("i = " + std::to_string(i) + ", size = " + std::to_string(sets[i].Size(n_workers)));
   const std::string trace = flags.Str("trace", "");
@@ -55,9 +75,20 @@ int Main(const Flags& flags) {
         r.del.push_back(KmerSet<K, N, KeyType>::FromSortedBits(std::move(mg.del[i])));
       }
     } else {
-      std::vector<KmerSet<K, N, KeyType>> ksets;
-      for (const auto& c : sets) ksets.push_back(c.ToKmerSet(canonical, n_workers));
+      {
+        const auto t_init = std::chrono::steady_clock::now();
+        Device::Check(kmsc_ctx_sync(Device::Ctx()), "kmsc_ctx_sync");
+        Info("device context ready, seconds = " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count()));
+      }
+      const auto t_dec = std::chrono::steady_clock::now();
+      std::vector<KmerSet<K, N, KeyType>> ksets = KmerSetCompact<K, N, KeyType>::ToKmerSetBatch(sets, canonical);
+      const auto t_mst = std::chrono::steady_clock::now();
       r = BuildMst<K, N, KeyType>(ksets);
+      Device::Check(kmsc_ctx_sync(Device::Ctx()), "kmsc_ctx_sync");
+      const auto t_end = std::chrono::steady_clock::now();
+      Info("phases: load files = " + std::to_string(s_load) + " s, decode = " +
+           std::to_string(std::chrono::duration<double>(t_mst - t_dec).count()) + " s, matrix + tree + splits = " +
+           std::to_string(std::chrono::duration<double>(t_end - t_mst).count()) + " s");
     }
     Info("constructed the spanning tree, edges = " + std::to_string(r.edges.size()));
     if (!trace.empty()) {
@@ -71,9 +102,12 @@ int Main(const Flags& flags) {
           << r.add[i].Size() << ' ' << r.add[i].Hash(n_workers) << ' ' << r.del[i].Size() << ' ' << r.del[i].Hash(n_workers) << "\n";
     }
     if (!out.empty() && !sets.empty()) {
+      const auto t_dump = std::chrono::steady_clock::now();
       Status st = DumpMst<K, N, KeyType>(r, sets[0], static_cast<int>(sets.size()), out, flags.Str("compressor", ""),
                                          flags.Str("extension", "txt"), canonical, n_workers);
       if (!st.ok()) { Error("failed to dump the spanning tree: " + st.ToString()); return 1; }
+      Info("dumped the spanning tree (SPSS of the root and of both difference sets of every edge), seconds = " +
+           std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dump).count()));
     }
     return 0;
   }
