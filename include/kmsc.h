@@ -174,6 +174,11 @@ int kmsc_set_neighbors(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int32_
 int kmsc_spss_build(kmsc_ctx* ctx, const kmsc_set* set, int canonical, int rounds, int64_t* n_strings,
                     int64_t* n_chars);
 int kmsc_spss_fetch(kmsc_ctx* ctx, char* text, int64_t* str_offs);
+/* The same result in the container KmerSetCompact holds (lib/core/kmer_set_compact.h:206-255): words
+ * ((n_chars + 31) / 32 uint64: 2 bits per base, 32 bases per word, first base in the top bits, strings back
+ * to back -- what kmsc_set_from_packed reads) and str_offs in bases. Packed on the device: the text never
+ * crosses the bus. */
+int kmsc_spss_fetch_packed(kmsc_ctx* ctx, uint64_t* words, int64_t* str_offs);
 
 /* ---- P3: all-pairs intersection counts ------------------------------------------ */
 /* Replaces GetEdgeWeight and the initial all-pairs loop of KmerSetSet's

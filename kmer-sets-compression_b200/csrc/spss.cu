@@ -214,6 +214,27 @@ __global__ void emit_kernel(const KeyT* __restrict__ keys, const uint32_t* __res
   if (blockIdx.x == 0 && threadIdx.x == 0) str_offs[sidx[n]] = (long long)soff[n];
 }
 
+// text (one byte per base, strings back to back) -> 2 bits per base, 32 bases per word, first base in the top
+// bits: the container KmerSetCompact holds (kmsc_set_from_packed reads the same layout)
+__global__ void pack_text_kernel(const char* __restrict__ text, long long n_chars, unsigned long long* __restrict__ words,
+                                 long long n_words) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  unsigned long long v = 0;
+  const long long base = w * 32;
+#pragma unroll 8
+  for (int j = 0; j < 32; j++) {
+    unsigned long long code = 0;
+    if (base + j < n_chars) {
+      const unsigned ch = (unsigned char)text[base + j];
+      code = (ch >> 1) & 3u;      // A 0, C 1, T 2, G 3 ...
+      code ^= code >> 1;          // ... -> A 0, C 1, G 2, T 3
+    }
+    v = (v << 2) | code;
+  }
+  words[w] = v;
+}
+
 }  // namespace
 }  // namespace kmsc
 
@@ -340,6 +361,25 @@ extern "C" int kmsc_spss_fetch(kmsc_ctx* ctx, char* text, int64_t* str_offs) {
   const size_t chars = (size_t)ctx->spss_chars;
   const unsigned char* base = (const unsigned char*)ctx->spss_out.p;
   KMSC_CUDA(cudaMemcpyAsync(text, base, chars, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaMemcpyAsync(str_offs, base + ((chars + 63) & ~(size_t)63), (size_t)(ctx->spss_strings + 1) * 8,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return KMSC_OK;
+}
+
+extern "C" int kmsc_spss_fetch_packed(kmsc_ctx* ctx, uint64_t* words, int64_t* str_offs) {
+  if (!ctx || !str_offs || (ctx->spss_chars > 0 && !words)) { set_error("NULL argument"); return KMSC_E_INVALID; }
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->spss_strings == 0) { str_offs[0] = 0; return KMSC_OK; }
+  const size_t chars = (size_t)ctx->spss_chars;
+  const long long n_words = (long long)((chars + 31) / 32);
+  const unsigned char* base = (const unsigned char*)ctx->spss_out.p;
+  KMSC_TRY(ctx->work2.reserve((size_t)n_words * 8 + 64));
+  unsigned long long* d_words = (unsigned long long*)ctx->work2.p;
+  pack_text_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, ctx->stream>>>((const char*)base, (long long)chars, d_words, n_words);
+  count_launch(ctx);
+  KMSC_CUDA(cudaGetLastError());
+  KMSC_CUDA(cudaMemcpyAsync(words, d_words, (size_t)n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
   KMSC_CUDA(cudaMemcpyAsync(str_offs, base + ((chars + 63) & ~(size_t)63), (size_t)(ctx->spss_strings + 1) * 8,
                             cudaMemcpyDeviceToHost, ctx->stream));
   KMSC_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -24,10 +24,34 @@ class KmerSetCompact {
  public:
   KmerSetCompact() = default;
 
-  static KmerSetCompact FromKmerSet(const KmerSet<K, N, KeyType>& kmer_set, bool canonical, bool fast, int n_workers) {
-    std::vector<std::string> spss =
-        canonical ? GetSPSSCanonical<K, N, KeyType>(kmer_set, fast, n_workers) : GetSPSS<K, N, KeyType>(kmer_set, n_workers);
-    return KmerSetCompact(spss);
+  // SPSS of the set, built AND packed on the device (kmsc_spss_build + kmsc_spss_fetch_packed): what comes back is
+  // this container's own 2-bit words and the string boundaries; no text crosses the bus (the reference:
+  // GetSPSSCanonical / GetSPSS, then the constructor's per-base packing, lib/core/kmer_set_compact.h:89-118).
+  static KmerSetCompact FromKmerSet(const KmerSet<K, N, KeyType>& kmer_set, bool canonical, bool /*fast*/, int /*n_workers*/) {
+    KmerSetCompact c;
+    if (kmer_set.Size() == 0) {
+      c.words_.assign(2, 0);
+      c.lengths_compressed_ = Svb0124Encode(std::vector<std::uint32_t>());
+      return c;
+    }
+    std::int64_t n_strings = 0, n_chars = 0;
+    std::vector<std::int64_t> offs;
+    {
+      const SetPtr dev = kmer_set.Dev();
+      std::lock_guard<std::mutex> l(Device::Mu());
+      Device::Check(kmsc_spss_build(Device::Ctx(), dev->set, canonical ? 1 : 0, /*rounds=*/0, &n_strings, &n_chars), "kmsc_spss_build");
+      c.words_.assign(static_cast<std::size_t>((n_chars + 31) / 32 + 2), 0);
+      offs.resize(static_cast<std::size_t>(n_strings) + 1);
+      Device::Check(kmsc_spss_fetch_packed(Device::Ctx(), c.words_.data(), offs.data()), "kmsc_spss_fetch_packed");
+    }
+    c.n_ = n_strings;
+    c.n_bases_ = n_chars;
+    std::vector<std::uint32_t> lengths(static_cast<std::size_t>(n_strings));
+    for (std::int64_t i = 0; i < n_strings; i++)
+      lengths[static_cast<std::size_t>(i)] = static_cast<std::uint32_t>(offs[static_cast<std::size_t>(i) + 1] - offs[static_cast<std::size_t>(i)]) -
+                                            static_cast<std::uint32_t>(K);
+    c.lengths_compressed_ = Svb0124Encode(lengths);
+    return c;
   }
   static KmerSetCompact FromStrings(const std::vector<std::string>& spss) { return KmerSetCompact(spss); }
 

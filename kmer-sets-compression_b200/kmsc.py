@@ -30,7 +30,7 @@ EXPORTS = [
     "kmsc_last_error", "kmsc_version", "kmsc_ctx_create", "kmsc_ctx_destroy", "kmsc_ctx_sync",
     "kmsc_ctx_stream", "kmsc_ctx_launch_count", "kmsc_set_from_csr", "kmsc_set_from_kmers",
     "kmsc_set_to_csr", "kmsc_set_free", "kmsc_set_size", "kmsc_set_hash", "kmsc_set_info",
-    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_spss_build", "kmsc_spss_fetch", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
+    "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_spss_build", "kmsc_spss_fetch", "kmsc_spss_fetch_packed", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
     "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host", "kmsc_host_alloc_pinned", "kmsc_host_free_pinned",
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.kmsc_set_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
     L.kmsc_spss_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.kmsc_spss_fetch.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
+    L.kmsc_spss_fetch_packed.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
     L.kmsc_set_bucket_offsets.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, _i64p]
     L.kmsc_set_export_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.kmsc_set_import_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -345,6 +346,15 @@ class Context:
         _check(lib().kmsc_spss_fetch(self.h, text, offs.ctypes.data_as(_i64p)))
         raw = text.raw
         return [raw[offs[i]:offs[i + 1]].decode() for i in range(ns.value)]
+
+    def spss_build_packed(self, s: DeviceSet, canonical=True, rounds=0):
+        """SPSS of a set as (words, str_offs): the packed container kmsc_set_from_packed reads"""
+        ns, nc = C.c_int64(0), C.c_int64(0)
+        _check(lib().kmsc_spss_build(self.h, s.h, int(canonical), int(rounds), C.byref(ns), C.byref(nc)))
+        words = np.zeros((nc.value + 31) // 32 + 2, np.uint64)
+        offs = np.zeros(ns.value + 1, np.int64)
+        _check(lib().kmsc_spss_fetch_packed(self.h, words.ctypes.data_as(_u64p), offs.ctypes.data_as(_i64p)))
+        return words, offs
 
     # -- multi-GPU inside the library -----------------------------------------------------------
     @staticmethod

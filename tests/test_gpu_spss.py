@@ -141,3 +141,24 @@ def test_spss_size_vs_reference(ctx, oracle, ref):
     ours_chars, theirs_chars = sum(map(len, ours)), sum(map(len, theirs))
     print(f"SPSS of {len(km)} 15-mers: ours {len(ours)} strings / {ours_chars} chars, reference {len(theirs)} / {theirs_chars}")
     assert ours_chars <= 1.15 * theirs_chars
+
+
+@pytest.mark.parametrize("K,canonical", [(23, True), (9, False), (31, True)])
+def test_spss_fetch_packed(ctx, oracle, K, canonical):
+    """kmsc_spss_fetch_packed = the strings of kmsc_spss_fetch packed 2 bits per base, 32 per word, first base in
+    the top bits, strings back to back (KmerSetCompact's container), and decodes to the set through kmsc_set_from_packed"""
+    import synth
+    from test_gpu_decode_batch import pack
+    N = N_OF[K]
+    km = np.unique(np.concatenate([synth.kmers_of(s, K, canonical) for s in synth.phylogeny_sequences(3, 30000, p=0.01, seed=K + 1)]))
+    offs, keys = synth.csr_of(km, K, N, KB[K])
+    s = ctx.set_from_csr(K, N, KB[K], offs, keys)
+    strs = ctx.spss_build(s, canonical=canonical)
+    words, str_offs = ctx.spss_build_packed(s, canonical=canonical)
+    want_words, want_offs = pack(strs)
+    nw = (int(str_offs[-1]) + 31) // 32
+    assert np.array_equal(str_offs, want_offs) and np.array_equal(words[:nw], want_words[:nw])
+    back = ctx.set_from_packed(K, N, KB[K], words, str_offs, canonical=canonical)
+    assert np.array_equal(back.to_kmers(), km)
+    back.free()
+    s.free()

@@ -72,4 +72,24 @@ for i in sorted(ksets):
     assert (sizes[i], hashes[i]) == (len(ksets[i]), o.set_hash(ksets[i])), i
 print(f"decompressed sets {sorted(ksets)}: size and XOR hash equal the originals; dump = {sum(f.stat().st_size for f in Path(out).iterdir()) / 1e6:.0f} MB "
       f"for {sum(os.path.getsize(f) for f in files) / 1e6:.0f} MB of input")
+# ---- the reference's own driver (greedy merges over sampled weights, lib/core/kmer_set_set.h:109-427) on the same files
+if len(sys.argv) > 3 and sys.argv[3] == "greedy":
+    out2 = os.path.join(tmp, "dump_greedy")
+    t = time.time()
+    r = subprocess.run([str(bins / "kmerset-multiple-compress"), f"--k={K}", "--seed=11", f"--workers={os.cpu_count()}", f"--out={out2}"] + files,
+                       capture_output=True, text=True, env=dict(os.environ, KMSC_TIMING="1"))
+    print(f"kmerset-multiple-compress (greedy, 2 % bucket sample): rc={r.returncode}, wall {time.time() - t:.2f} s")
+    for l in r.stderr.split("\n"):
+        if "timing" in l or "seconds" in l or "rror" in l:
+            print("   ", l)
+    assert r.returncode == 0
+    t = time.time()
+    r = subprocess.run([str(bins / "kmerset-multiple-decompress"), f"--k={K}", f"--n={n_sets}", out2], capture_output=True, text=True)
+    print(f"kmerset-multiple-decompress of all {n_sets} sets: rc={r.returncode}, wall {time.time() - t:.2f} s")
+    assert r.returncode == 0, r.stderr[-500:]
+    hashes = [int(x) for x in re.findall(r"kmer_set.Hash\(\) = (\d+)", r.stderr)]
+    sizes = [int(x) for x in re.findall(r"kmer_set.Size\(\) = (\d+)", r.stderr)]
+    for i in sorted(ksets):
+        assert (sizes[i], hashes[i]) == (len(ksets[i]), o.set_hash(ksets[i])), i
+    print(f"greedy dump: decompressed sets {sorted(ksets)} equal the originals; {sum(f.stat().st_size for f in Path(out2).iterdir()) / 1e6:.0f} MB")
 shutil.rmtree(tmp)
