@@ -345,13 +345,19 @@ class KmerSetSetReader {
       if (it == children_.end()) continue;
       for (int c : it->second) q.push(c);
     }
+    // a node is read, packed and decoded once: its device set stays with the reader (merge nodes are shared by
+    // many of the original sets; the reference re-reads them for every Get)
     std::vector<KmerSet<K, N, KeyType>> parts;
     int n_fail = 0;
     for (int id : ids) {
-      const std::string f = (std::filesystem::path(directory_name_) / (std::to_string(id) + "." + extension_)).string();
-      StatusOr<KmerSetCompact<K, N, KeyType>> c = KmerSetCompact<K, N, KeyType>::Load(f, decompressor_);
-      if (!c.ok()) { n_fail++; continue; }
-      parts.push_back(c.value().ToKmerSet(canonical_, n_workers));
+      auto hit = cache_.find(id);
+      if (hit == cache_.end()) {
+        const std::string f = (std::filesystem::path(directory_name_) / (std::to_string(id) + "." + extension_)).string();
+        StatusOr<KmerSetCompact<K, N, KeyType>> c = KmerSetCompact<K, N, KeyType>::Load(f, decompressor_);
+        if (!c.ok()) { n_fail++; continue; }
+        hit = cache_.emplace(id, c.value().ToKmerSet(canonical_, n_workers)).first;
+      }
+      parts.push_back(hit->second);
     }
     if (n_fail > 0) return InternalError("failed to load data from " + std::to_string(n_fail) + " files");
     return KmerSetSet<K, N, KeyType>::Union(parts);
@@ -362,6 +368,7 @@ class KmerSetSetReader {
   bool canonical_ = false;
   internal::AdjacencyList children_;
   int size_ = 0;
+  mutable std::map<int, KmerSet<K, N, KeyType>> cache_;   // node id -> device set
 };
 
 // ---- mst driver ---------------------------------------------------------------------------
@@ -508,22 +515,31 @@ class MstReader {
   // S_i = ((S_root \ del) | add) applied along the tree path from the root to i
   StatusOr<KmerSet<K, N, KeyType>> Get(int i, int n_workers) const {
     using Compact = KmerSetCompact<K, N, KeyType>;
+    // walk up to the nearest set this reader has already reconstructed (the root at the latest), then apply the
+    // edges of the path downwards; every set on the way stays with the reader, so reconstructing all n sets
+    // reads every file once
     std::vector<int> path;
-    for (int c = i; c != 0; c = parent_[static_cast<std::size_t>(c)]) {
-      if (c < 0 || path.size() > parent_.size()) return InternalError("malformed tree");
+    int c = i;
+    while (c != 0 && cache_.find(c) == cache_.end()) {
+      if (c < 0 || c >= size_ || path.size() > parent_.size()) return InternalError("malformed tree");
       path.push_back(c);
+      c = parent_[static_cast<std::size_t>(c)];
     }
     const std::filesystem::path dir(directory_name_);
-    StatusOr<Compact> root = Compact::Load((dir / ("0." + extension_)).string(), decompressor_);
-    if (!root.ok()) return root.status();
-    KmerSet<K, N, KeyType> s = root.value().ToKmerSet(canonical_, n_workers);
+    if (c == 0 && cache_.find(0) == cache_.end()) {
+      StatusOr<Compact> root = Compact::Load((dir / ("0." + extension_)).string(), decompressor_);
+      if (!root.ok()) return root.status();
+      cache_.emplace(0, root.value().ToKmerSet(canonical_, n_workers));
+    }
+    KmerSet<K, N, KeyType> s = cache_.at(c);
     for (auto it = path.rbegin(); it != path.rend(); ++it) {
-      const std::string c = std::to_string(*it);
-      StatusOr<Compact> add = Compact::Load((dir / (c + ".add." + extension_)).string(), decompressor_);
-      StatusOr<Compact> del = Compact::Load((dir / (c + ".del." + extension_)).string(), decompressor_);
+      const std::string name = std::to_string(*it);
+      StatusOr<Compact> add = Compact::Load((dir / (name + ".add." + extension_)).string(), decompressor_);
+      StatusOr<Compact> del = Compact::Load((dir / (name + ".del." + extension_)).string(), decompressor_);
       if (!add.ok() || !del.ok()) return InternalError("failed to load data from 1 files");
       s.Sub(del.value().ToKmerSet(canonical_, n_workers), n_workers);
       s.Add(add.value().ToKmerSet(canonical_, n_workers), n_workers);
+      cache_.emplace(*it, s);
     }
     return s;
   }
@@ -533,6 +549,7 @@ class MstReader {
   bool canonical_ = false;
   int size_ = 0;
   std::vector<int> parent_;
+  mutable std::map<int, KmerSet<K, N, KeyType>> cache_;   // set id -> reconstructed device set
 };
 
 }  // namespace kmsc
