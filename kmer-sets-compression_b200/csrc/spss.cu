@@ -37,13 +37,15 @@ namespace {
 constexpr int kFree = -1;
 constexpr uint32_t kEnd = 0x80000000u;   // low word of a jump entry: the walk's end has been reached (n < 2^30 k-mers)
 
+// position of k-mer w in the set, or -1. `fine` is the set's finest offset level (2^(N+F) + 1 entries, fine bucket
+// = the top N + F bits of the k-mer): the binary search runs over the ~10 keys of one fine bucket, not over a bucket.
 template <typename KeyT>
-__device__ __forceinline__ int32_t find_kmer(const KeyT* __restrict__ keys, const uint32_t* __restrict__ offs,
-                                             unsigned long long w, int key_bits, unsigned long long kmask) {
-  const uint32_t bq = (uint32_t)(w >> key_bits);
+__device__ __forceinline__ int32_t find_kmer(const KeyT* __restrict__ keys, const uint32_t* __restrict__ fine,
+                                             unsigned long long w, int fine_shift, unsigned long long kmask) {
+  const uint32_t x = (uint32_t)(w >> fine_shift);
   const unsigned long long kq = w & kmask;
-  uint32_t a = offs[bq];
-  const uint32_t end = offs[bq + 1];
+  uint32_t a = fine[x];
+  const uint32_t end = fine[x + 1];
   uint32_t e = end;
   while (a < e) {
     const uint32_t mid = (a + e) >> 1;
@@ -54,8 +56,8 @@ __device__ __forceinline__ int32_t find_kmer(const KeyT* __restrict__ keys, cons
 
 // cand[8 i + 4 p + c]: the port reached from port p of k-mer i with base c, or -1 (absent, or i itself).
 template <typename KeyT>
-__global__ void cand_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ offs, int n_buckets,
-                            int K, int key_bits, int canonical, int32_t* __restrict__ cand) {
+__global__ void cand_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ offs, const uint32_t* __restrict__ fine,
+                            int fine_shift, int n_buckets, int K, int key_bits, int canonical, int32_t* __restrict__ cand) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const unsigned long long mask = K == 32 ? ~0ull : ((1ull << (2 * K)) - 1);
@@ -74,7 +76,7 @@ __global__ void cand_kernel(const KeyT* __restrict__ keys, const uint32_t* __res
           const unsigned long long rc = revcomp(w, K);
           if (rc < w) { w = rc; flip = 1; }
         }
-        const int32_t j = find_kmer(keys, offs, w, key_bits, kmask);
+        const int32_t j = find_kmer(keys, fine, w, fine_shift, kmask);
         // a right extension enters the successor through its left port (0), a left extension through the
         // right port (1); the other one when the set holds the reverse complement of the extension
         int32_t q = -1;
@@ -102,11 +104,12 @@ __global__ void propose_kernel(const int32_t* __restrict__ cand, const int32_t* 
 }
 
 // mutual proposals become links
-__global__ void accept_kernel(const int32_t* __restrict__ prop, int64_t n_ports, int32_t* __restrict__ link) {
+__global__ void accept_kernel(const int32_t* __restrict__ prop, int64_t n_ports, int32_t* __restrict__ link,
+                              int* __restrict__ linked) {
   const int64_t P = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (P >= n_ports) return;
   const int32_t Q = prop[P];
-  if (Q >= 0 && prop[Q] == (int32_t)P) link[P] = Q;
+  if (Q >= 0 && prop[Q] == (int32_t)P) { link[P] = Q; *linked = 1; }
 }
 
 // walk state s = 2 i + p (k-mer i left through port p): successor and distance, packed (dist << 32 | succ).
@@ -129,6 +132,79 @@ __global__ void jump_kernel(unsigned long long* __restrict__ jump, int64_t n_sta
   const unsigned long long b = jump[(uint32_t)a];   // one aligned 8-byte load: a consistent (successor, distance) pair
   jump[s] = (((a >> 32) + (b >> 32)) << 32) | (unsigned long long)(uint32_t)b;
   *changed = 1;
+}
+
+// ---- work-efficient ranking: splitters -------------------------------------------------------
+// Pointer jumping over all 2 n states costs a random 8-byte load and store per state per round, ~15 rounds.
+// Instead: a state is a SPLITTER if its walk starts there (the port behind it is free) or a hash of its id
+// says so (1 in 64). (1) every splitter walks to the next splitter or the end of its walk (~64 dependent
+// loads, hundreds of thousands of walkers in flight), (2) pointer jumping runs over the splitters only,
+// (3) every splitter walks its segment again and writes the final (distance, end) of each state it passes.
+// A cycle holds no start splitter: its states stay unwritten (or its sampled splitters never reach an end);
+// the caller counts them and, if there are any, takes the full pointer jumping with cycle cutting below.
+__device__ __forceinline__ bool sampled_splitter(uint32_t s) { return ((s * 0x9E3779B1u) >> 26) == 0u; }
+
+__global__ void split_walk_kernel(const int32_t* __restrict__ link, int64_t n_states, unsigned long long* __restrict__ sj,
+                                  uint32_t* __restrict__ list, uint32_t* __restrict__ n_list, uint32_t cap) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_states) return;
+  if (link[s ^ 1] != kFree && !sampled_splitter((uint32_t)s)) return;
+  uint32_t cur = (uint32_t)s, d = 0;
+  unsigned long long out = 0;
+  for (;;) {
+    const int32_t Q = link[cur];
+    if (Q == kFree) { out = ((unsigned long long)d << 32) | (unsigned long long)(cur | kEnd); break; }
+    const uint32_t nxt = (uint32_t)(Q ^ 1);
+    d++;
+    if (sampled_splitter(nxt)) { out = ((unsigned long long)d << 32) | (unsigned long long)nxt; break; }
+    if (d > (1u << 24)) { out = ((unsigned long long)d << 32) | (unsigned long long)nxt; break; }   // (a long splitter-free cycle: left unresolved)
+    cur = nxt;
+  }
+  sj[s] = out;
+  const uint32_t at = atomicAdd(n_list, 1u);
+  if (at < cap) list[at] = (uint32_t)s;
+}
+
+__global__ void split_jump_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, uint32_t cap,
+                                  unsigned long long* __restrict__ sj, int* __restrict__ changed) {
+  const uint32_t n = min(*n_list, cap);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t s = list[t];
+  const unsigned long long a = sj[s];
+  if ((uint32_t)a & kEnd) return;
+  const unsigned long long b = sj[(uint32_t)a];
+  sj[s] = (((a >> 32) + (b >> 32)) << 32) | (unsigned long long)(uint32_t)b;
+  *changed = 1;
+}
+
+__global__ void split_fill_kernel(const int32_t* __restrict__ link, const uint32_t* __restrict__ list,
+                                  const uint32_t* __restrict__ n_list, uint32_t cap, const unsigned long long* __restrict__ sj,
+                                  unsigned long long* __restrict__ jump) {
+  const uint32_t n = min(*n_list, cap);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t s = list[t];
+  const unsigned long long a = sj[s];
+  if (!((uint32_t)a & kEnd)) return;     // on a cycle
+  const uint32_t E = (uint32_t)a;
+  uint32_t D = (uint32_t)(a >> 32), cur = s;
+  for (;;) {
+    jump[cur] = ((unsigned long long)D << 32) | (unsigned long long)E;
+    const int32_t Q = link[cur];
+    if (Q == kFree) break;
+    const uint32_t nxt = (uint32_t)(Q ^ 1);
+    if (sampled_splitter(nxt) || D == 0) break;
+    D--;
+    cur = nxt;
+  }
+}
+
+__global__ void count_unranked_kernel(const unsigned long long* __restrict__ jump, int64_t n_states, unsigned long long* __restrict__ n_bad) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bad = s < n_states && !((uint32_t)jump[s] & kEnd);
+  const unsigned b = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_bad, (unsigned long long)__popc(b));
 }
 
 // states that did not reach a free port lie on cycles: (smallest state seen << 32 | successor)
@@ -251,6 +327,7 @@ extern "C" int kmsc_spss_build(kmsc_ctx* ctx, const kmsc_set* set, int canonical
   *n_chars = 0;
   const int64_t n = set->n_keys;
   if (n == 0) return KMSC_OK;
+  KMSC_TRY(set_ensure_levels(ctx, set));
   if ((double)n * set->K >= 4.0e9) { set_error("SPSS text may exceed 2^32 characters"); return KMSC_E_INVALID; }
   KMSC_CUDA(cudaSetDevice(ctx->device));
   const int64_t np = 2 * n;
@@ -284,27 +361,70 @@ extern "C" int kmsc_spss_build(kmsc_ctx* ctx, const kmsc_set* set, int canonical
   if (bblocks > ctx->sm_count * 16) bblocks = ctx->sm_count * 16;
   const unsigned pblocks = (unsigned)((np + 255) / 256), nblocks = (unsigned)((n + 255) / 256);
   switch (set->key_bytes) {
-    case 2: cand_kernel<uint16_t><<<bblocks, 256, 0, ctx->stream>>>((const uint16_t*)set->keys, set->lev[0], nb, set->K, set->key_bits, canonical, d_cand); break;
-    case 4: cand_kernel<uint32_t><<<bblocks, 256, 0, ctx->stream>>>((const uint32_t*)set->keys, set->lev[0], nb, set->K, set->key_bits, canonical, d_cand); break;
-    default: cand_kernel<unsigned long long><<<bblocks, 256, 0, ctx->stream>>>((const unsigned long long*)set->keys, set->lev[0], nb, set->K, set->key_bits, canonical, d_cand); break;
+    case 2: cand_kernel<uint16_t><<<bblocks, 256, 0, ctx->stream>>>((const uint16_t*)set->keys, set->lev[0], set->lev[set->max_level], set->key_bits - set->max_level, nb, set->K, set->key_bits, canonical, d_cand); break;
+    case 4: cand_kernel<uint32_t><<<bblocks, 256, 0, ctx->stream>>>((const uint32_t*)set->keys, set->lev[0], set->lev[set->max_level], set->key_bits - set->max_level, nb, set->K, set->key_bits, canonical, d_cand); break;
+    default: cand_kernel<unsigned long long><<<bblocks, 256, 0, ctx->stream>>>((const unsigned long long*)set->keys, set->lev[0], set->lev[set->max_level], set->key_bits - set->max_level, nb, set->K, set->key_bits, canonical, d_cand); break;
   }
   count_launch(ctx);
   KMSC_CUDA(cudaMemsetAsync(d_link, 0xFF, (size_t)np * 4, ctx->stream));
-  for (int r = 0; r < rounds; r++) {
-    propose_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_cand, d_link, np, d_prop);
-    accept_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_prop, np, d_link);
-    count_launch(ctx, 2);
-  }
-  KMSC_CUDA(cudaGetLastError());
-
   void* pin = nullptr;
   KMSC_TRY(ctx_pinned(ctx, 64, &pin));
   int* h_changed = (int*)pin;
+  // the first two rounds join nearly every port that can be joined; from then on a round that made no link
+  // ends the matching (read back every second round)
+  for (int r = 0; r < rounds; r++) {
+    if (r >= 2 && (r & 1) == 0) KMSC_CUDA(cudaMemsetAsync(d_changed, 0, 4, ctx->stream));
+    propose_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_cand, d_link, np, d_prop);
+    accept_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_prop, np, d_link, d_changed);
+    count_launch(ctx, 2);
+    if (r >= 3 && (r & 1) == 1 && r + 1 < rounds) {
+      KMSC_CUDA(cudaMemcpyAsync(h_changed, d_changed, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (*h_changed == 0) break;
+    }
+  }
+  KMSC_CUDA(cudaGetLastError());
+
   unsigned long long* h_ncut = (unsigned long long*)((unsigned char*)pin + 8);
   uint32_t* h_totals = (uint32_t*)((unsigned char*)pin + 16);
   int log2n = 1;
   while ((1ll << log2n) < np) log2n++;
-  for (int attempt = 0; attempt < 3; attempt++) {
+  // fast path: ranking through splitters; complete unless the links hold a cycle
+  bool ranked = false;
+  {
+    unsigned long long* d_sj = (unsigned long long*)(base + o_cand);   // the candidate table is dead: (next, distance) of the splitters
+    uint32_t* d_list = (uint32_t*)(base + o_prop);                     // the proposals are dead: the list of splitters
+    uint32_t* d_nlist = (uint32_t*)(base + o_misc + 32);
+    const uint32_t cap = (uint32_t)np;
+    KMSC_CUDA(cudaMemsetAsync(d_nlist, 0, 4, ctx->stream));
+    KMSC_CUDA(cudaMemsetAsync(d_jump, 0, (size_t)np * 8, ctx->stream));
+    split_walk_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_link, np, d_sj, d_list, d_nlist, cap);
+    count_launch(ctx);
+    // splitters are ~1 / 32 of the states (starts + 1 in 64): a grid over np / 8 threads covers any list
+    const unsigned lblocks = (unsigned)((np / 8 + 255) / 256 + 1);
+    uint32_t* h_nlist = (uint32_t*)((unsigned char*)pin + 32);
+    KMSC_CUDA(cudaMemcpyAsync(h_nlist, d_nlist, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((uint64_t)*h_nlist <= (uint64_t)lblocks * 256) {
+      bool converged = false;
+      for (int r = 0; r < log2n + 6 && !converged; r += 4) {
+        KMSC_CUDA(cudaMemsetAsync(d_changed, 0, 4, ctx->stream));
+        for (int k = 0; k < 4; k++) split_jump_kernel<<<lblocks, 256, 0, ctx->stream>>>(d_list, d_nlist, cap, d_sj, d_changed);
+        count_launch(ctx, 4);
+        KMSC_CUDA(cudaMemcpyAsync(h_changed, d_changed, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+        converged = *h_changed == 0;
+      }
+      KMSC_CUDA(cudaMemsetAsync(d_ncut, 0, 8, ctx->stream));
+      split_fill_kernel<<<lblocks, 256, 0, ctx->stream>>>(d_link, d_list, d_nlist, cap, d_sj, d_jump);
+      count_unranked_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_jump, np, d_ncut);
+      count_launch(ctx, 2);
+      KMSC_CUDA(cudaMemcpyAsync(h_ncut, d_ncut, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+      ranked = *h_ncut == 0;
+    }
+  }
+  for (int attempt = 0; attempt < 3 && !ranked; attempt++) {
     jump_init_kernel<<<pblocks, 256, 0, ctx->stream>>>(d_link, np, d_jump);
     count_launch(ctx);
     bool converged = false;
