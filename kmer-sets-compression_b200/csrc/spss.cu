@@ -15,12 +15,16 @@
 //             the later rounds stitch unitigs the way the greedy path cover does. Links are symmetric, one per
 //             port, never from a k-mer to itself: the result is a set of paths and (rarely) cycles.
 //   ranking   a walk state 2 i + p = "k-mer i, left through port p". The successor of a state is fixed by the
-//             link, so pointer jumping over packed (successor, distance) words gives every state the free port
-//             its walk ends at and the distance to it, in place and without double buffering. Each path is
-//             walked from both ends; the walk that starts at the smaller free port wins, and a k-mer reads its
-//             position and its start off the losing walk (which ends where the winning one begins).
-//   cycles    states that never reach a free port: a second pointer jumping carries the smallest state of the
-//             cycle, the link leaving that state is cut, and the ranking is redone.
+//             link. Every state needs the free port its walk ends at and the distance to it. Work-efficient
+//             path: a state is a splitter if its walk starts there or a hash of its id says so (1 in 64); every
+//             splitter walks to the next one, pointer jumping over packed (successor, distance) words runs over
+//             the splitters only (in place, no double buffering), every splitter walks its segment again and
+//             writes the result of each state it passes. Each path is walked from both ends; the walk that
+//             starts at the smaller free port wins, and a k-mer reads its position and its start off the losing
+//             walk (which ends where the winning one begins).
+//   cycles    hold no start splitter, so some state stays unranked: then all states are ranked by plain pointer
+//             jumping, the ones that never reach a free port lie on cycles, a second jumping pass carries the
+//             smallest state of each cycle, the link leaving that state is cut, and the ranking is redone.
 //   emission  string lengths at the start k-mers -> exclusive scan -> every k-mer writes its K bases (start) or
 //             its last base in walk orientation at offset(start) + K - 1 + position.
 // Output is deterministic for a given set: strings ordered by their start k-mer.
@@ -107,9 +111,11 @@ __global__ void propose_kernel(const int32_t* __restrict__ cand, const int32_t* 
 __global__ void accept_kernel(const int32_t* __restrict__ prop, int64_t n_ports, int32_t* __restrict__ link,
                               int* __restrict__ linked) {
   const int64_t P = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= n_ports) return;
-  const int32_t Q = prop[P];
-  if (Q >= 0 && prop[Q] == (int32_t)P) { link[P] = Q; *linked = 1; }
+  const int32_t Q = P < n_ports ? prop[P] : -1;
+  const bool join = Q >= 0 && prop[Q] == (int32_t)P;
+  if (join) link[P] = Q;
+  // one store per warp that linked anything, not one per port (millions of stores to one address)
+  if (__any_sync(__activemask(), join) && (threadIdx.x & 31) == 0) *linked = 1;
 }
 
 // walk state s = 2 i + p (k-mer i left through port p): successor and distance, packed (dist << 32 | succ).
