@@ -6,6 +6,9 @@
 // per finest-level fine bucket does it: pass 1 counts per fine bucket, a device scan turns the
 // counts into the output's finest-level offsets (they ARE its fine index), pass 2 writes the keys.
 // (The split n = j & k, j \ n, k \ n and KmerSet::Diff are the single-pass kernel of pair_split.cu.)
+#include <algorithm>
+#include <vector>
+
 #include "kmsc_common.cuh"
 #include "scan.cuh"
 
@@ -269,6 +272,102 @@ int counted_union(kmsc_ctx* ctx, const kmsc_set* a, const uint8_t* ca, const kms
 
 using namespace kmsc;
 
+// ---- union of up to kUnionMax sets in ONE pair of passes ---------------------------------------
+// KmerSetSet::Get / KmerSetSetReader::Get unite every node reachable from a set (reference
+// lib/core/kmer_set_set.h:433-454, 672-755: a fold of Add); a left fold of two-way unions reads and rewrites
+// the growing result m - 1 times. Here a thread owns one finest-level fine bucket and merges the m runs
+// (~10 keys each) directly: the smallest head is written once and every run holding it advances.
+constexpr int kUnionMax = 16;
+struct UnionArgs {
+  const void* keys[kUnionMax];
+  const uint32_t* lev[kUnionMax];
+};
+
+template <typename KeyT, int M, bool WRITE>
+__global__ void union_multi_kernel(UnionArgs ua, int m, uint32_t NF, uint32_t* __restrict__ cnt /* counts (pass 1) / offsets (pass 2) */,
+                                   KeyT* __restrict__ out) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= NF) return;
+  uint32_t i[M], e[M];
+  unsigned long long h[M];   // head key, or 2^64 - 1 once the run is exhausted (keys are at most 63 bits wide)
+  const unsigned long long INF = ~0ull;
+#pragma unroll
+  for (int t = 0; t < M; t++) {
+    i[t] = 0; e[t] = 0; h[t] = INF;
+    if (t < m) {
+      i[t] = ua.lev[t][x];
+      e[t] = ua.lev[t][x + 1];
+      if (i[t] < e[t]) h[t] = (unsigned long long)reinterpret_cast<const KeyT*>(ua.keys[t])[i[t]];
+    }
+  }
+  uint32_t n = 0, p = WRITE ? cnt[x] : 0u;
+  for (;;) {
+    unsigned long long g = h[0];
+#pragma unroll
+    for (int t = 1; t < M; t++) g = h[t] < g ? h[t] : g;
+    if (g == INF) break;
+    if (WRITE) out[p++] = (KeyT)g; else n++;
+#pragma unroll
+    for (int t = 0; t < M; t++) {
+      if (h[t] == g) {
+        i[t]++;
+        h[t] = i[t] < e[t] ? (unsigned long long)reinterpret_cast<const KeyT*>(ua.keys[t])[i[t]] : INF;
+      }
+    }
+  }
+  if (!WRITE) cnt[x] = n;
+}
+
+template <typename KeyT, bool WRITE>
+static void launch_union_multi(kmsc_ctx* ctx, const UnionArgs& ua, int m, uint32_t NF, uint32_t* cnt, void* out) {
+  const unsigned blocks = (NF + 127) / 128;
+  if (m <= 4) union_multi_kernel<KeyT, 4, WRITE><<<blocks, 128, 0, ctx->stream>>>(ua, m, NF, cnt, (KeyT*)out);
+  else if (m <= 8) union_multi_kernel<KeyT, 8, WRITE><<<blocks, 128, 0, ctx->stream>>>(ua, m, NF, cnt, (KeyT*)out);
+  else union_multi_kernel<KeyT, 16, WRITE><<<blocks, 128, 0, ctx->stream>>>(ua, m, NF, cnt, (KeyT*)out);
+  count_launch(ctx);
+}
+
+// union of sets[0 .. m), 2 <= m <= kUnionMax (duplicate-free inputs of one shape, levels present)
+static int union_multi(kmsc_ctx* ctx, const kmsc_set* const* sets, int m, kmsc_set** out) {
+  const kmsc_set* a = sets[0];
+  const int F = a->max_level;
+  const uint32_t NF = (uint32_t)1 << (a->N + F);
+  const size_t ent = (size_t)NF + 1;
+  const size_t sb = scan_scratch_entries(NF);
+  KMSC_TRY(ctx->work2.reserve((ent + sb + 16) * 4));
+  uint32_t* d_cnt = (uint32_t*)ctx->work2.p;
+  uint32_t* d_bsum = d_cnt + ent;
+  uint32_t* d_total = d_bsum + sb;
+  UnionArgs ua{};
+  for (int t = 0; t < m; t++) { ua.keys[t] = sets[t]->keys; ua.lev[t] = sets[t]->lev[F]; }
+  switch (a->key_bytes) {
+    case 2: launch_union_multi<uint16_t, false>(ctx, ua, m, NF, d_cnt, nullptr); break;
+    case 4: launch_union_multi<uint32_t, false>(ctx, ua, m, NF, d_cnt, nullptr); break;
+    default: launch_union_multi<unsigned long long, false>(ctx, ua, m, NF, d_cnt, nullptr); break;
+  }
+  KMSC_CUDA(cudaGetLastError());
+  KMSC_TRY(exclusive_scan_u32(ctx, d_cnt, d_cnt, NF, d_bsum, d_total));
+  void* pin = nullptr;
+  KMSC_TRY(ctx_pinned(ctx, 64, &pin));
+  KMSC_CUDA(cudaMemcpyAsync(pin, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t nu = *(uint32_t*)pin;
+  kmsc_set* u = nullptr;
+  uint32_t* src[1] = {d_cnt};
+  KMSC_TRY(sets_from_fine_offsets(ctx, a, 1, &nu, src, NF, &u));
+  switch (a->key_bytes) {
+    case 2: launch_union_multi<uint16_t, true>(ctx, ua, m, NF, d_cnt, u->keys); break;
+    case 4: launch_union_multi<uint32_t, true>(ctx, ua, m, NF, d_cnt, u->keys); break;
+    default: launch_union_multi<unsigned long long, true>(ctx, ua, m, NF, d_cnt, u->keys); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  // the offsets in work2 are read by the write pass and the level fill: both are queued; callers that reuse
+  // work2 do so on the same stream
+  if (e != cudaSuccess) { kmsc_set_free(ctx, u); return cuda_fail(e, "union write", __FILE__, __LINE__); }
+  *out = u;
+  return KMSC_OK;
+}
+
 extern "C" {
 
 int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_set** out) {
@@ -278,6 +377,46 @@ int kmsc_set_union(kmsc_ctx* ctx, const kmsc_set* const* sets, int32_t m, kmsc_s
     if (!sets[t]) { set_error("sets[%d] is NULL", t); return KMSC_E_INVALID; }
     KMSC_TRY(set_check_dups(ctx, const_cast<kmsc_set*>(sets[t])));
     if (sets[t]->has_dups == 1) { set_error("sets[%d] holds duplicate keys (union needs true sets)", t); return KMSC_E_INVALID; }
+  }
+  if (m >= 3) {
+    // groups of up to kUnionMax sets per pass pair; the partial unions are united the same way
+    for (int32_t t = 0; t < m; t++) {
+      int rc = check_pair(sets[0], sets[t]);
+      if (rc == KMSC_OK) rc = set_ensure_levels(ctx, sets[t]);
+      if (rc != KMSC_OK) return rc;
+    }
+    std::vector<const kmsc_set*> cur(sets, sets + m);
+    std::vector<kmsc_set*> owned;   // intermediates of the previous round
+    while (cur.size() > 1) {
+      std::vector<const kmsc_set*> next;
+      std::vector<kmsc_set*> made;
+      for (size_t a = 0; a < cur.size(); a += kUnionMax) {
+        const int g = (int)std::min<size_t>(kUnionMax, cur.size() - a);
+        if (g == 1) { next.push_back(cur[a]); continue; }
+        kmsc_set* u = nullptr;
+        const int rc = union_multi(ctx, cur.data() + a, g, &u);
+        if (rc != KMSC_OK) {
+          for (kmsc_set* x : made) kmsc_set_free(ctx, x);
+          for (kmsc_set* x : owned) kmsc_set_free(ctx, x);
+          return rc;
+        }
+        made.push_back(u);
+        next.push_back(u);
+      }
+      // an intermediate that was carried over unchanged (a group of one) stays alive for the next round
+      std::vector<kmsc_set*> keep;
+      for (kmsc_set* x : owned) {
+        bool carried = false;
+        for (const kmsc_set* y : next) carried |= y == x;
+        if (carried) keep.push_back(x); else kmsc_set_free(ctx, x);
+      }
+      owned = keep;
+      owned.insert(owned.end(), made.begin(), made.end());
+      cur = next;
+    }
+    KMSC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = const_cast<kmsc_set*>(cur[0]);
+    return KMSC_OK;
   }
   // left fold of two-way unions; intermediates are freed as we go
   kmsc_set* acc = nullptr;

@@ -155,3 +155,4 @@ def test_batch_low_complexity_long_runs(ctx, oracle, path):
     assert np.array_equal(go, wo) and np.array_equal(gk.astype(np.uint64), wk)
     d = ctx.sets_from_packed_batch(K, N, 4, [words], [offs], canonical=False, dedup=True)[0]
     assert np.array_equal(d.to_kmers(), oracle.set_from_spss(strs, K, False))
+

@@ -372,3 +372,26 @@ def test_split_and_union_refuse_multisets(ctx):
         with pytest.raises(kmsc.KmscError):
             call()
     assert ctx.set_union([plain, plain]).Size() == 3
+
+
+@pytest.mark.parametrize("m", [3, 8, 16, 17, 40])
+def test_multiway_union(ctx, oracle, m):
+    """kmsc_set_union of m >= 3 sets: one pass pair per group of <= 16 (thread per finest bucket merging the m
+    runs) instead of a left fold; equal to the numpy union, incl. empty and identical inputs"""
+    import synth
+    K, N = 23, 14
+    rng = np.random.default_rng(m)
+    seqs = synth.phylogeny_sequences(m, 20000, p=0.02, seed=100 + m)
+    kms = [synth.kmer_set_of(s, K) for s in seqs]
+    kms[1] = np.zeros(0, np.uint64)
+    kms[2] = kms[0].copy()
+    dev = []
+    for km in kms:
+        offs, keys = synth.csr_of(km, K, N, 4)
+        dev.append(ctx.set_from_csr(K, N, 4, offs, keys))
+    u = ctx.set_union(dev)
+    want = np.unique(np.concatenate(kms))
+    assert np.array_equal(u.to_kmers(), want)
+    assert u.Hash() == oracle.set_hash(want)
+    # the result is a full set: it feeds the other kernels
+    assert int(ctx.pair_counts([u, dev[0]])[0, 1]) == len(kms[0])
