@@ -334,6 +334,8 @@ extern "C" int kmsc_spss_build(kmsc_ctx* ctx, const kmsc_set* set, int canonical
   const int64_t n = set->n_keys;
   if (n == 0) return KMSC_OK;
   KMSC_TRY(set_ensure_levels(ctx, set));
+  if (set->has_dups < 0) KMSC_TRY(set_check_dups(ctx, const_cast<kmsc_set*>(set)));
+  if (set->has_dups == 1) { set_error("the set holds duplicate keys (an SPSS spells every k-mer once: build it from a true set)"); return KMSC_E_INVALID; }
   if ((double)n * set->K >= 4.0e9) { set_error("SPSS text may exceed 2^32 characters"); return KMSC_E_INVALID; }
   KMSC_CUDA(cudaSetDevice(ctx->device));
   const int64_t np = 2 * n;

@@ -162,3 +162,13 @@ def test_spss_fetch_packed(ctx, oracle, K, canonical):
     assert np.array_equal(back.to_kmers(), km)
     back.free()
     s.free()
+
+
+def test_spss_refuses_multisets(ctx):
+    """a device set built with dedup = 0 from a text that repeats a k-mer is a multiset: no SPSS of it"""
+    import kmsc
+    K, N = 23, 14
+    s = ctx.set_from_spss(K, N, 4, ["ACGTACGTTGCATGCAAGCTTGCATTT", "ACGTACGTTGCATGCAAGCTTGCATTT"], canonical=True, dedup=False)
+    with pytest.raises(kmsc.KmscError):
+        ctx.spss_build(s)
+    s.free()
