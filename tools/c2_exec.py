@@ -32,10 +32,11 @@ print(f"{n_sets} SPSS files, {sum(os.path.getsize(f) for f in files) / 1e6:.0f} 
 bins = ROOT / "kmer-sets-compression_b200" / "host" / "bin"
 out, trace = os.path.join(tmp, "dump"), os.path.join(tmp, "trace.txt")
 t = time.time()
+n_gpus = int(os.environ.get("GPUS", "1"))
 r = subprocess.run([str(bins / "kmerset-multiple-compress"), f"--k={K}", "--driver=mst", f"--workers={os.cpu_count()}", f"--out={out}",
-                    f"--trace={trace}"] + files, capture_output=True, text=True)
+                    f"--trace={trace}"] + ([f"--gpus={n_gpus}"] if n_gpus > 1 else []) + files, capture_output=True, text=True)
 wall = time.time() - t
-print(f"kmerset-multiple-compress --driver=mst: rc={r.returncode}, wall {wall:.2f} s")
+print(f"kmerset-multiple-compress --driver=mst{f' --gpus={n_gpus}' if n_gpus > 1 else ''}: rc={r.returncode}, wall {wall:.2f} s")
 for l in r.stderr.split("\n"):
     if "phases" in l or "seconds" in l or "edges" in l or "rror" in l:
         print("   ", l)
