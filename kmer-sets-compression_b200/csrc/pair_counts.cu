@@ -255,7 +255,13 @@ template <int NS, int TKB> struct PcCfg;
 #endif
 template <int TKB> struct PcCfg<64, TKB>  { static constexpr int S = 1 << PC_LOG2S64, LOG2S = PC_LOG2S64, D = PC_D64, T = 256,  CK = PC_CK64, UNR = PC_UNR64, MINB = PC_MINB64; };
 template <int TKB> struct PcCfg<128, TKB> { static constexpr int S = 2048, LOG2S = 11, D = 1280, T = 512,  CK = 4, UNR = 4, MINB = 2; };
-template <> struct PcCfg<256, 4>          { static constexpr int S = 4096, LOG2S = 12, D = 2560, T = 1024, CK = 4, UNR = 2, MINB = 1; };
+#ifndef PC_UNR256
+#define PC_UNR256 2
+#endif
+#ifndef PC_D256
+#define PC_D256 2560
+#endif
+template <> struct PcCfg<256, 4>          { static constexpr int S = 4096, LOG2S = 12, D = PC_D256, T = 1024, CK = 4, UNR = PC_UNR256, MINB = 1; };
 template <> struct PcCfg<256, 8>          { static constexpr int S = 2048, LOG2S = 11, D = 1280, T = 1024, CK = 4, UNR = 2, MINB = 1; };
 
 constexpr int kStackMax = 48;
