@@ -76,6 +76,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stage", action="store_true")
     ap.add_argument("--profile-e2e", action="store_true", help="diagnostic: per-phase times of the e2e step on stderr (synchronises between phases)")
+    ap.add_argument("--e2e-pieces", type=int, default=4, help="multi-GPU e2e: pieces of a rank's sets whose exchange overlaps the decode of the next piece")
+    ap.add_argument("--no-e2e-overlap", action="store_true", help="multi-GPU e2e: exchange after the whole decode instead of overlapping the two halves")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle check of W at full size")
     ap.add_argument("--no-c1", action="store_true", help="skip the bounded C1 end-to-end run of the executable")
     ap.add_argument("--emulate", default="", help="diagnostic, one GPU: R/W = the shard rank R of a W-rank job would hold")
@@ -890,7 +892,41 @@ def main():
             for s in ss + full:
                 s.free()
 
-        step_e2e = step_e2e_exchange if m_own > 0 else step_e2e_single
+        # The same step with the exchange overlapped with the decode: a second context (its own stream, no
+        # communicator) decodes, the first one exchanges.
+        ctx2 = None
+        if m_own >= 2 and not args.no_e2e_overlap:
+            stream2 = torch.cuda.Stream(device=dev)
+            ctx2 = kmsc.Context(local_rank, stream2.cuda_stream)
+
+        def step_e2e_overlap():
+            # P pieces of the rank's sets: piece p is exchanged (thread, first context) while piece p + 1 is decoded
+            # (second context); a piece is an independent collection of len(piece) * world sets, and the outputs of
+            # the pieces concatenate to the global set order (global id = rank + j * world)
+            P = min(args.e2e_pieces, m_own)
+            mine = [rank + j * world for j in range(m_own)]
+            bounds = [m_own * q // P for q in range(P + 1)]
+            outs, fulls, th = [None] * P, [], None
+
+            def ex(q, full):
+                outs[q] = ctx.sets_exchange(full, cuts_np, len(full) * world)
+            for q in range(P):
+                ids = mine[bounds[q]:bounds[q + 1]]
+                full = ctx2.sets_from_packed_batch(K, N, KB, None, [str_offs] * len(ids), words_ptrs=[pinned[i].data_ptr() for i in ids])
+                ctx2.sync()
+                fulls += full
+                if th is not None:
+                    th.join()
+                th = threading.Thread(target=ex, args=(q, full))
+                th.start()
+            th.join()
+            ss = [s_ for o in outs for s_ in o]
+            ctx.pair_counts_device(ss, d_out.data_ptr())
+            host_out[:] = d_out.cpu().numpy().reshape(n, n)
+            for s_ in ss + fulls:
+                s_.free()
+
+        step_e2e = (step_e2e_overlap if ctx2 is not None and not args.profile_e2e else step_e2e_exchange) if m_own > 0 else step_e2e_single
 
         for s in sets:
             s.free()
@@ -937,7 +973,8 @@ def main():
         e2e = {"value": visits_total * e2e_steps / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(nbytes_in // world) if m_own > 0 else int(nbytes_in),
                "how": ("decode split by set over the ranks (kmsc_sets_from_packed_batch) + kmsc_sets_exchange (one grouped NCCL send/recv of "
-                       "the prefix slices) + kmsc_pair_counts_device (all-reduce inside)"
+                       "the prefix slices) + kmsc_pair_counts_device (all-reduce inside)" + (f"; the rank's sets go in {min(args.e2e_pieces, m_own)} pieces: a piece is "
+                       "exchanged while a second context decodes the next one" if ctx2 is not None and not args.profile_e2e else "")
                        if m_own > 0 else "every rank decodes its prefix range of every set"),
                "d2h_bytes_per_step": int(n * n * 8), "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps}
 
