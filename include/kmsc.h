@@ -275,6 +275,11 @@ int kmsc_count_last_counts(kmsc_ctx* ctx, uint8_t* out, int64_t n);
 typedef struct kmsc_counter kmsc_counter;
 int kmsc_counter_create(kmsc_ctx* ctx, int K, int N, int key_bytes, int canonical, kmsc_counter** out);
 int kmsc_counter_add_fasta(kmsc_ctx* ctx, kmsc_counter* c, const char* fasta, int64_t n_bytes);
+/* Optional: announce the chunk that will be added NEXT. Its host-to-device copy starts at once on the context's
+ * copy stream and overlaps the counting of the chunk added in between; the following kmsc_counter_add_* call
+ * with the same pointer and size uses the copy (any other call ignores it). The buffer must stay unchanged
+ * until that add call returns; page-locked memory (kmsc_host_alloc_pinned) makes the copy asynchronous. */
+int kmsc_counter_prefetch(kmsc_ctx* ctx, kmsc_counter* c, const char* text, int64_t n_bytes);
 int kmsc_counter_add_reads(kmsc_ctx* ctx, kmsc_counter* c, const char* reads, int64_t n_bytes);
 int kmsc_counter_finish(kmsc_ctx* ctx, kmsc_counter* c, int cutoff, kmsc_set** out, int64_t* cutoff_count,
                         int64_t* n_distinct);

@@ -191,8 +191,12 @@ int filter_t(kmsc_ctx* ctx, const kmsc_set* full, const uint8_t* d_counts, int c
   return KMSC_OK;
 }
 
+// d_text_ready != NULL: the text is on the device already (kmsc_counter_prefetch copied it on the copy stream while
+// the previous chunk was counted; the caller has made ctx->stream wait for that copy); `text` is still read on
+// the host for the last byte
 int count_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, int64_t n, int canonical,
-                 int cutoff, int fasta, kmsc_set** out, int64_t* cutoff_count, int64_t* n_distinct) {
+                 int cutoff, int fasta, kmsc_set** out, int64_t* cutoff_count, int64_t* n_distinct,
+                 const unsigned char* d_text_ready = nullptr) {
   if (!ctx || !out || n < 0 || (n > 0 && !text)) { set_error("bad argument"); return KMSC_E_INVALID; }
   if (K < 1 || K > 32 || N < 0 || N > 24 || N > 2 * K || 2 * K - N > 8 * key_bytes || 2 * K - N >= 64 ||
       (key_bytes != 2 && key_bytes != 4 && key_bytes != 8)) { set_error("bad K/N/key_bytes"); return KMSC_E_INVALID; }
@@ -204,7 +208,7 @@ int count_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, i
 
   const unsigned long long n_chunks = ((unsigned long long)n + 31) / 32;
   size_t off = 0;
-  const size_t o_text = off; off += ((size_t)n + 255) & ~(size_t)255;
+  const size_t o_text = off; off += d_text_ready ? 256 : (((size_t)n + 255) & ~(size_t)255);
   const size_t o_nl = off; off += ((size_t)(n_chunks + 1) * 4 + 255) & ~(size_t)255;
   const size_t o_bsum = off; off += (scan_scratch_entries(n_chunks) * 4 + 255) & ~(size_t)255;
   const size_t o_words = off; off += ((size_t)(n_chunks + 2) * 8 + 255) & ~(size_t)255;
@@ -213,7 +217,7 @@ int count_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, i
   const size_t o_flag = off; off += 256;
   KMSC_TRY(ctx->stage.reserve(off));
   unsigned char* base = (unsigned char*)ctx->stage.p;
-  unsigned char* d_text = base + o_text;
+  const unsigned char* d_text = d_text_ready ? d_text_ready : base + o_text;
   uint32_t* d_nl = (uint32_t*)(base + o_nl);
   uint32_t* d_bsum = (uint32_t*)(base + o_bsum);
   unsigned long long* d_words = (unsigned long long*)(base + o_words);
@@ -221,7 +225,7 @@ int count_common(kmsc_ctx* ctx, int K, int N, int key_bytes, const char* text, i
   uint32_t* d_bad = (uint32_t*)(base + o_bad);
   int* d_flag = (int*)(base + o_flag);          // [0] flags, [1] total newlines
 
-  if (n > 0) KMSC_CUDA(cudaMemcpyAsync(d_text, text, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if (n > 0 && !d_text_ready) KMSC_CUDA(cudaMemcpyAsync(base + o_text, text, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   KMSC_CUDA(cudaMemsetAsync(d_flag, 0, 16, ctx->stream));
   KMSC_CUDA(cudaMemsetAsync(d_words + n_chunks, 0, 16, ctx->stream));
   const int threads = 128;
@@ -335,6 +339,13 @@ struct kmsc_counter {
   int K, N, key_bytes, canonical;
   kmsc_set* acc;        // all distinct k-mers so far
   uint8_t* counts;      // device, aligned with acc's keys
+  // chunks announced by kmsc_counter_prefetch: their text on the device, copied on the copy stream. Two slots:
+  // the chunk being added may itself sit in one while the next one is copied into the other
+  struct Pre {
+    const char* host = nullptr;
+    int64_t n = 0;
+  } pre[2];   // slot q's bytes live in ctx->pre_buf[q], its copy is marked by ctx->pre_ev[q]
+  int pre_next = 0;
 };
 
 int kmsc_counter_create(kmsc_ctx* ctx, int K, int N, int key_bytes, int canonical, kmsc_counter** out) {
@@ -355,7 +366,16 @@ static int counter_add(kmsc_ctx* ctx, kmsc_counter* c, const char* text, int64_t
   if (!ctx || !c) { set_error("NULL argument"); return KMSC_E_INVALID; }
   kmsc_set* s = nullptr;
   int64_t cut = 0, nd = 0;
-  KMSC_TRY(count_common(ctx, c->K, c->N, c->key_bytes, text, n, c->canonical, /*cutoff=*/1, fasta, &s, &cut, &nd));
+  const unsigned char* ready = nullptr;
+  for (int q = 0; q < 2; q++) {
+    kmsc_counter::Pre& p = c->pre[q];
+    if (p.host && p.host == text && p.n == n && n > 0 && !ready) {
+      KMSC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pre_ev[q], 0));
+      ready = (const unsigned char*)ctx->pre_buf[q].p;
+      p.host = nullptr;   // consumed (the slot is reused by the prefetch after next)
+    }
+  }
+  KMSC_TRY(count_common(ctx, c->K, c->N, c->key_bytes, text, n, c->canonical, /*cutoff=*/1, fasta, &s, &cut, &nd, ready));
   // count_common left the chunk's counter in the context (borrowed set + owned counts): take both
   uint8_t* sc = ctx->last_counts;
   ctx->last_counts = nullptr; ctx->last_counted = nullptr; ctx->last_counted_owned = false;
@@ -369,6 +389,32 @@ static int counter_add(kmsc_ctx* ctx, kmsc_counter* c, const char* text, int64_t
   kmsc_set_free(ctx, c->acc);
   if (c->counts) cudaFree(c->counts);
   c->acc = u; c->counts = uc;
+  return KMSC_OK;
+}
+
+int kmsc_counter_prefetch(kmsc_ctx* ctx, kmsc_counter* c, const char* text, int64_t n_bytes) {
+  if (!ctx || !c || n_bytes < 0 || (n_bytes > 0 && !text)) { set_error("bad argument"); return KMSC_E_INVALID; }
+  if (n_bytes == 0) return KMSC_OK;
+  KMSC_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    KMSC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->copy_ev) KMSC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    KMSC_CUDA(cudaEventCreateWithFlags(&ctx->fence_ev, cudaEventDisableTiming));
+  }
+  const int q = c->pre_next;
+  kmsc_counter::Pre& p = c->pre[q];
+  c->pre_next ^= 1;
+  p.host = nullptr;
+  if (!ctx->pre_ev[q]) KMSC_CUDA(cudaEventCreateWithFlags(&ctx->pre_ev[q], cudaEventDisableTiming));
+  if (ctx->pre_buf[q].cap < (size_t)n_bytes) KMSC_CUDA(cudaStreamSynchronize(ctx->stream));   // growing frees the old buffer: its readers are on the main stream
+  KMSC_TRY(ctx->pre_buf[q].reserve((size_t)n_bytes));
+  // the slot's last reader (the classify kernels of the chunk it held before) ran on the main stream
+  KMSC_CUDA(cudaEventRecord(ctx->fence_ev, ctx->stream));
+  KMSC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->fence_ev, 0));
+  KMSC_CUDA(cudaMemcpyAsync(ctx->pre_buf[q].p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  KMSC_CUDA(cudaEventRecord(ctx->pre_ev[q], ctx->copy_stream));
+  p.host = text;
+  p.n = n_bytes;
   return KMSC_OK;
 }
 
@@ -414,6 +460,8 @@ int kmsc_counter_finish(kmsc_ctx* ctx, kmsc_counter* c, int cutoff, kmsc_set** o
 
 void kmsc_counter_free(kmsc_ctx* ctx, kmsc_counter* c) {
   if (!c) return;
+  // a copy announced but never used may still be in flight out of the caller's buffer
+  if ((c->pre[0].host || c->pre[1].host) && ctx && ctx->copy_stream) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->copy_stream); }
   if (c->acc) kmsc_set_free(ctx, c->acc);
   if (c->counts) cudaFree(c->counts);
   delete c;

@@ -366,7 +366,7 @@ void kmsc_ctx_destroy(kmsc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   kmsc_comm_destroy(ctx);
-  ctx->plan.release(); ctx->work.release(); ctx->work2.release(); ctx->work3.release(); ctx->stage.release(); ctx->small.release(); ctx->spss_out.release(); for (int i = 0; i < kmsc_ctx::kP2Slots; i++) {
+  ctx->plan.release(); ctx->work.release(); ctx->work2.release(); ctx->work3.release(); ctx->stage.release(); ctx->small.release(); ctx->spss_out.release(); ctx->pre_buf[0].release(); ctx->pre_buf[1].release(); for (auto& e : ctx->pre_ev) if (e) cudaEventDestroy(e); for (int i = 0; i < kmsc_ctx::kP2Slots; i++) {
     ctx->p2a[i].release(); ctx->p2b[i].release(); ctx->p2tab[i].release(); ctx->p2rb[i].release();
     if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
   }

@@ -62,6 +62,8 @@ struct kmsc_ctx {
   kmsc::Scratch stage;    // input staging (text, packed bases)
   kmsc::Scratch small;    // small per-call device arrays (descriptors, ids)
   kmsc::Scratch spss_out; // result of the last kmsc_spss_build: text, then string offsets
+  kmsc::Scratch pre_buf[2];   // kmsc_counter_prefetch: device copies of announced chunks (grow-only: no malloc / free per counter)
+  cudaEvent_t pre_ev[2] = {nullptr, nullptr};
   int64_t spss_strings = 0, spss_chars = 0;
   // staged partition sort: up to kP2Slots groups of jobs in flight, each with its own tables
   static constexpr int kP2Slots = 4;

@@ -129,7 +129,11 @@ class KmerCounter {
     auto run = [&](auto&& sink) {
       if (ov && std::atoi(ov) == 0) return ReadRecordChunks(file_name, decompressor, chunk_bytes, sink);
       if (ov && std::atoi(ov) == 1) return ReadRecordChunksOverlapped(file_name, decompressor, chunk_bytes, sink);
-      return ReadRecordChunksPinned(file_name, decompressor, chunk_bytes, sink);
+      return ReadRecordChunksPinned(file_name, decompressor, chunk_bytes, sink, [&](const char* data, std::size_t n) {
+        // the chunk after this one is already in its page-locked buffer: its copy overlaps the counting of this one
+        std::lock_guard<std::mutex> l(Device::Mu());
+        kmsc_counter_prefetch(Device::Ctx(), c, data, static_cast<std::int64_t>(n));
+      });
     };
     const bool timing = std::getenv("KMSC_TIMING") != nullptr;
     if (timing) {   // the process's first CUDA call (context start-up) is kept out of the phase times

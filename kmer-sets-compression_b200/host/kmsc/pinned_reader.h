@@ -22,9 +22,13 @@
 
 namespace kmsc {
 
-template <typename Sink>
+// `announce(data, n)` (optional) is told about the chunk that will be handed to `sink` NEXT, when it is already
+// waiting, before the current one is processed: the device counter starts its copy (kmsc_counter_prefetch).
+struct NoAnnounce { void operator()(const char*, std::size_t) const {} };
+
+template <typename Sink, typename Announce = NoAnnounce>
 inline Status ReadRecordChunksPinned(const std::string& file_name, const std::string& decompressor,
-                                     std::size_t chunk_bytes, Sink sink, int n_buffers = 3) {
+                                     std::size_t chunk_bytes, Sink sink, Announce announce = Announce(), int n_buffers = 3) {
   const std::size_t cap = chunk_bytes + (static_cast<std::size_t>(8) << 20);
   std::vector<char*> bufs;
   for (int i = 0; i < n_buffers; i++) {
@@ -117,14 +121,16 @@ inline Status ReadRecordChunksPinned(const std::string& file_name, const std::st
 
   Status st = OkStatus();
   for (;;) {
-    std::pair<int, std::size_t> item;
+    std::pair<int, std::size_t> item, next{-1, 0};
     {
       std::unique_lock<std::mutex> l(mu);
       cv.wait(l, [&] { return !full_q.empty() || done; });
       if (full_q.empty()) break;
       item = full_q.front();
       full_q.pop_front();
+      if (!full_q.empty()) next = full_q.front();   // stays in the queue: only this thread takes chunks out
     }
+    if (next.first >= 0) announce(bufs[next.first], next.second);
     st = sink(bufs[item.first], item.second);
     std::lock_guard<std::mutex> l(mu);
     if (!st.ok()) { stop = true; cv.notify_all(); break; }

@@ -33,7 +33,7 @@ EXPORTS = [
     "kmsc_set_from_spss", "kmsc_set_from_packed", "kmsc_sets_from_packed_batch", "kmsc_set_neighbors", "kmsc_spss_build", "kmsc_spss_fetch", "kmsc_spss_fetch_packed", "kmsc_comm_unique_id", "kmsc_comm_init", "kmsc_comm_destroy", "kmsc_comm_info", "kmsc_sets_exchange", "kmsc_set_bucket_offsets", "kmsc_set_export_range", "kmsc_set_import_range", "kmsc_pair_counts_stats", "kmsc_pair_counts_build", "kmsc_pair_counts", "kmsc_pair_counts_device", "kmsc_pair_counts_partial", "kmsc_pair_counts_rows",
     "kmsc_pair_split", "kmsc_pair_split_batch", "kmsc_set_union", "kmsc_set_diff", "kmsc_count_fasta", "kmsc_count_reads",
     "kmsc_count_get", "kmsc_count_last_counts", "kmsc_counter_create", "kmsc_counter_add_fasta",
-    "kmsc_counter_add_reads", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host", "kmsc_host_alloc_pinned", "kmsc_host_free_pinned",
+    "kmsc_counter_add_reads", "kmsc_counter_prefetch", "kmsc_counter_finish", "kmsc_counter_free", "kmsc_bitmap_gram", "kmsc_codec_encode", "kmsc_codec_decode", "kmsc_free_host", "kmsc_host_alloc_pinned", "kmsc_host_free_pinned",
 ]
 
 
@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
     L.kmsc_counter_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.kmsc_counter_add_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.kmsc_counter_add_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.kmsc_counter_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.kmsc_counter_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _i64p, _i64p]
     L.kmsc_counter_free.argtypes = [C.c_void_p, C.c_void_p]
     L.kmsc_counter_free.restype = None
@@ -445,15 +446,19 @@ class Context:
         _check(lib().kmsc_count_get(self.h, kmer, C.byref(v)))
         return v.value
 
-    def count_chunks(self, K, N, key_bytes, chunks, canonical=True, cutoff=1, fasta=True):
+    def count_chunks(self, K, N, key_bytes, chunks, canonical=True, cutoff=1, fasta=True, prefetch=True):
         """streaming counter: every chunk holds whole records; returns (set, cutoff_count, n_distinct)"""
         c = C.c_void_p()
         _check(lib().kmsc_counter_create(self.h, K, N, key_bytes, int(canonical), C.byref(c)))
         try:
             add = lib().kmsc_counter_add_fasta if fasta else lib().kmsc_counter_add_reads
-            for ch in chunks:   # bytes, or a uint8 numpy view (e.g. of pinned memory)
-                ptr = ch.ctypes.data if isinstance(ch, np.ndarray) else C.cast(C.c_char_p(ch), C.c_void_p)
-                _check(add(self.h, c, ptr, len(ch)))
+            # bytes, or uint8 numpy views (e.g. of pinned memory); the copy of chunk i + 1 is announced before
+            # chunk i is counted (kmsc_counter_prefetch)
+            ptrs = [ch.ctypes.data if isinstance(ch, np.ndarray) else C.cast(C.c_char_p(ch), C.c_void_p).value for ch in chunks]
+            for i, ch in enumerate(chunks):
+                if prefetch and i + 1 < len(chunks) and not os.environ.get("KMSC_NO_PREFETCH"):
+                    _check(lib().kmsc_counter_prefetch(self.h, c, C.c_void_p(ptrs[i + 1]), len(chunks[i + 1])))
+                _check(add(self.h, c, C.c_void_p(ptrs[i]), len(ch)))
             h, cut, nd = C.c_void_p(), C.c_int64(), C.c_int64()
             _check(lib().kmsc_counter_finish(self.h, c, cutoff, C.byref(h), C.byref(cut), C.byref(nd)))
         finally:

@@ -171,3 +171,46 @@ def test_streaming_counter_errors_and_empty(ctx):
     with pytest.raises(kmsc.KmscError) as ei:
         ctx.count_chunks(15, 14, 2, [b">a\nACGT\n", b">b\nACGu\n"], canonical=True, cutoff=1)
     assert "invalid FASTA file" in str(ei.value)
+
+
+def test_streaming_counter_prefetch(ctx, oracle):
+    """kmsc_counter_prefetch (the next chunk's copy overlaps the counting of the current one): same counts with
+    and without it, with announcements that are not followed up (another pointer is added) and repeated ones"""
+    import ctypes as C
+    import kmsc
+    K, N = 23, 14
+    rng = np.random.default_rng(3)
+    base = "".join(rng.choice(list("ACGT"), 30000))
+    chunks, reads = [], []
+    for c in range(5):
+        lines = []
+        for i in range(400):
+            a = int(rng.integers(0, 29700))
+            r = base[a:a + int(rng.integers(30, 250))]
+            reads.append(r)
+            lines += [f">c{c}r{i}", r]
+        chunks.append(np.frombuffer(("\n".join(lines) + "\n").encode(), np.uint8).copy())
+    kmers, counts = oracle.count_reads(reads, K, True)
+    kept, cut = oracle.counter_to_set(kmers, counts, 2)
+    for prefetch in (True, False):
+        s, gcut, nd = ctx.count_chunks(K, N, 4, chunks, canonical=True, cutoff=2, fasta=True, prefetch=prefetch)
+        assert nd == len(kmers) and gcut == cut and np.array_equal(s.to_kmers(), kept)
+        s.free()
+    # announcements out of order / never used
+    L = kmsc.lib()
+    c = C.c_void_p()
+    assert L.kmsc_counter_create(ctx.h, K, N, 4, 1, C.byref(c)) == 0
+    ptr = lambda a: C.c_void_p(a.ctypes.data)
+    assert L.kmsc_counter_prefetch(ctx.h, c, ptr(chunks[3]), len(chunks[3])) == 0
+    assert L.kmsc_counter_prefetch(ctx.h, c, ptr(chunks[1]), len(chunks[1])) == 0
+    for i in (0, 1, 2):
+        assert L.kmsc_counter_add_fasta(ctx.h, c, ptr(chunks[i]), len(chunks[i])) == 0
+    assert L.kmsc_counter_prefetch(ctx.h, c, ptr(chunks[4]), len(chunks[4])) == 0
+    assert L.kmsc_counter_prefetch(ctx.h, c, ptr(chunks[4]), len(chunks[4])) == 0
+    for i in (3, 4):
+        assert L.kmsc_counter_add_fasta(ctx.h, c, ptr(chunks[i]), len(chunks[i])) == 0
+    h, cc, nd = C.c_void_p(), C.c_int64(), C.c_int64()
+    assert L.kmsc_counter_finish(ctx.h, c, 2, C.byref(h), C.byref(cc), C.byref(nd)) == 0
+    L.kmsc_counter_free(ctx.h, c)
+    s = kmsc.DeviceSet(ctx, h.value)
+    assert nd.value == len(kmers) and cc.value == cut and np.array_equal(s.to_kmers(), kept)
