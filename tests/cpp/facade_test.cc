@@ -274,9 +274,36 @@ static void TestDisjointSet() {  // test/parallel_disjoint_set.cc
     std::fflush(stdout);                          \
   } while (0)
 
-int main() {
+// streamvbyte-0124 byte codes of the string lengths (host/kmsc/streamvbyte0124.h): round trip, and the bytes of a
+// fixed vector printed for tests/test_host_facade.py to compare with the oracle's restatement
+static void TestSvb0124() {
+  std::vector<std::uint32_t> v;
+  for (int i = 0; i < 1000; i++) {
+    const int kind = static_cast<int>(rng() % 4);
+    v.push_back(kind == 0 ? 0u : kind == 1 ? static_cast<std::uint32_t>(rng() & 0xff) : kind == 2 ? static_cast<std::uint32_t>(rng() & 0xffff)
+                                                                                            : static_cast<std::uint32_t>(rng()));
+  }
+  const std::vector<std::uint8_t> enc = Svb0124Encode(v);
+  CHECK(Svb0124Decode(enc, v.size()) == v);
+  CHECK(Svb0124Decode(Svb0124Encode(std::vector<std::uint32_t>()), 0).empty());
+  std::vector<std::uint32_t> fixed;
+  for (std::uint32_t i = 0; i < 37; i++) fixed.push_back(i % 5 == 0 ? 0u : (i * 2654435761u) >> (i % 4 * 8));
+  std::printf("svb0124");
+  for (std::uint8_t b : Svb0124Encode(fixed)) std::printf(" %02x", b);
+  std::printf("\n");
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "--host-only") {   // no device call: the CPU suite runs these
+    RUN(TestKmer);
+    RUN(TestDisjointSet);
+    RUN(TestSvb0124);
+    if (g_fail == 0) std::printf("ALL OK\n");
+    return g_fail == 0 ? 0 : 1;
+  }
   RUN(TestKmer);
   RUN(TestDisjointSet);
+  RUN(TestSvb0124);
   RUN(TestKmerSet);
   RUN(TestKmerCounter);
   RUN(TestKmerSetCompact);
